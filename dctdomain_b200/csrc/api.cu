@@ -1,0 +1,36 @@
+// libdctd: version / error plumbing of the C ABI (include/dctd.h).
+#include "dctd_internal.cuh"
+
+namespace dctd {
+static thread_local cudaError_t g_last_cuda = cudaSuccess;
+static thread_local int64_t g_launches = 0;
+void set_cuda_error(cudaError_t e) { g_last_cuda = e; }
+void count_launch(int n) { g_launches += n; }
+}  // namespace dctd
+
+extern "C" {
+
+int dctd_version(void) { return DCTD_VERSION; }
+
+const char *dctd_strerror(int code) {
+    switch (code) {
+        case DCTD_OK: return "ok";
+        case DCTD_ERR_ARG: return "invalid argument";
+        case DCTD_ERR_CUDA: return "CUDA error (see dctd_last_cuda_error_string)";
+        case DCTD_ERR_WORKSPACE: return "workspace too small";
+        case DCTD_ERR_UNSUPPORTED: return "configuration not supported by this kernel set";
+        case DCTD_ERR_NOMEM: return "host allocation failed";
+        default: return "unknown dctd error code";
+    }
+}
+
+int dctd_last_cuda_error(void) { return (int)dctd::g_last_cuda; }
+const char *dctd_last_cuda_error_string(void) { return cudaGetErrorString(dctd::g_last_cuda); }
+
+int64_t dctd_launch_count(int reset) {
+    int64_t v = dctd::g_launches;
+    if (reset) dctd::g_launches = 0;
+    return v;
+}
+
+}  // extern "C"

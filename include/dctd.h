@@ -1,0 +1,145 @@
+/* dctd.h - C ABI of libdctd (B200 / sm_100a implementation of the two DCTdomain hot paths).
+ *
+ * The reference (mgtools/DCTdomain) is pure Python on these paths: there is no native
+ * interface to replace one-for-one.  Each entry point below states the reference code it
+ * stands in for (file:line under the reference tree); INTEGRATION.md shows the ctypes
+ * binding a reference maintainer would add.
+ *
+ * Conventions
+ *   - every function returns DCTD_OK (0) or a negative DCTD_ERR_* code, never throws or exits;
+ *   - pointers named d_* / "device" are device pointers on the CURRENT CUDA device, pointers
+ *     named h_* / "host" are host pointers; the caller owns every buffer including workspaces;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); all device work
+ *     is stream-ordered on it and the functions do not synchronise unless stated;
+ *   - the library keeps no global mutable state besides a thread-local "last CUDA error".
+ */
+#ifndef DCTD_H
+#define DCTD_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DCTD_VERSION 100
+
+#define DCTD_OK 0
+#define DCTD_ERR_ARG (-1)         /* invalid argument */
+#define DCTD_ERR_CUDA (-2)        /* a CUDA call failed: see dctd_last_cuda_error() */
+#define DCTD_ERR_WORKSPACE (-3)   /* workspace too small */
+#define DCTD_ERR_UNSUPPORTED (-4) /* valid in the reference, not supported by this kernel set */
+#define DCTD_ERR_NOMEM (-5)       /* host allocation failed */
+
+int dctd_version(void);
+const char *dctd_strerror(int code);
+/* cudaError_t of the last failing CUDA call on this thread (0 if none) and its string */
+int dctd_last_cuda_error(void);
+const char *dctd_last_cuda_error_string(void);
+/* number of kernel launches issued by this library on this thread since the last reset */
+int64_t dctd_launch_count(int reset);
+
+/* =====================================================================================
+ * Hot path 1: DCT fingerprints ("quant2D")
+ *   replaces reference src/fingerprint.py:110-201 (scale / idct_quant / get_doms / quantize)
+ *   and consumes the maxlen windows of src/embedding.py:153-192 directly (the 200-row overlap
+ *   average (prev+cur)/2 is applied while the rows are loaded).
+ *
+ * Geometry is described once per batch by a host-side plan:
+ *   sources   : n_src row-major float32 matrices [rows, D] per layer (one per protein, or one per
+ *               maxlen window of a protein); all layers share the geometry;
+ *   proteins  : protein p owns sources prot_src0[p] .. prot_src0[p]+prot_nsrc[p]-1; window c
+ *               covers protein rows [c*stride, c*stride + rows(window c)) with stride =
+ *               maxlen - overlap; rows covered by two windows are (a + b) * 0.5f;
+ *   domains   : domain i belongs to protein dom_prot[i] and is the concatenation, in listed
+ *               order, of its segments seg_beg[j] .. seg_end[j] (0-based, end exclusive,
+ *               j in [dom_seg_off[i], dom_seg_off[i+1])), exactly the row order that
+ *               get_doms (fingerprint.py:160-171) builds.
+ * Output: int8 [n_dom, out_stride] with layer l's n*m bytes at column l*n*m + j*m + c
+ *   (quantize's reshape(n*m) and per-layer extend, fingerprint.py:194-196).
+ * ===================================================================================== */
+typedef struct dctd_fp_plan dctd_fp_plan; /* opaque, host memory only */
+
+typedef struct dctd_fp_geometry {
+    int32_t n_layers;          /* embedding layers per source (reference: 2, layers 15 and 21) */
+    int32_t D;                 /* embedding width (1280 for ESM-2 t33, 640 for t30); D >= m */
+    int32_t n, m;              /* qdim pair applied to every layer (reference: 3, 80) */
+    int32_t maxlen, overlap;   /* window length / overlap of embedding.py:163-165 (500 / 200);
+                                  only used for proteins with more than one source */
+    int32_t n_src;
+    const int32_t *src_rows;   /* host [n_src] rows of each source */
+    int32_t n_prot;
+    const int32_t *prot_src0;  /* host [n_prot] */
+    const int32_t *prot_nsrc;  /* host [n_prot] */
+    int32_t n_dom;
+    const int32_t *dom_prot;    /* host [n_dom] */
+    const int32_t *dom_seg_off; /* host [n_dom+1] */
+    const int32_t *seg_beg;     /* host [n_seg] 0-based first row */
+    const int32_t *seg_end;     /* host [n_seg] exclusive end row (already clipped to the protein) */
+} dctd_fp_geometry;
+
+/* Builds the work decomposition (pieces, split items sorted longest first).  Host only. */
+int dctd_fp_plan_create(const dctd_fp_geometry *geo, dctd_fp_plan **out_plan);
+void dctd_fp_plan_destroy(dctd_fp_plan *plan);
+/* bytes of device workspace dctd_fp_execute needs for this plan */
+size_t dctd_fp_workspace_bytes(const dctd_fp_plan *plan);
+/* algorithmic input bytes of the plan: sum over domains of n_layers * L * D * 4 (roofline numerator) */
+int64_t dctd_fp_algorithmic_bytes(const dctd_fp_plan *plan);
+int32_t dctd_fp_num_items(const dctd_fp_plan *plan);
+
+#define DCTD_FP_TABLES_RESIDENT 1u /* the plan tables were already uploaded to this workspace by an
+                                      earlier dctd_fp_execute with the same plan: skip the copy */
+
+/* h_src_ptrs: host array [n_layers * n_src] of DEVICE pointers, layer-major
+ *             (h_src_ptrs[l * n_src + s] = rows of source s, layer l); row stride = ld elements.
+ * d_out     : device int8 [n_dom, out_stride], out_stride >= n_layers*n*m.
+ * Launches: 1 memset + (unless TABLES_RESIDENT) 1 H2D copy of the plan tables + 1 kernel. */
+int dctd_fp_execute(const dctd_fp_plan *plan, const void *const *h_src_ptrs, int64_t ld,
+                    int8_t *d_out, int64_t out_stride, void *d_workspace, size_t workspace_bytes,
+                    uint32_t flags, void *stream);
+
+/* =====================================================================================
+ * Hot path 2: exhaustive L1 top-k over int8 fingerprints
+ *   replaces faiss.IndexFlat + METRIC_L1 search as called at reference src/query_db.py:75-76,87
+ *   and bench/cathdb/run_dct.py:51-60 on the index built at src/database.py:240-243.
+ *   Result per query: the k smallest database positions by (distance, position), ascending;
+ *   unfilled slots are (FLT_MAX, -1).
+ *
+ * The database is kept on the device in a packed layout (groups of 32 vectors interleaved in
+ * 16-byte chunks, bytes biased by 0x80) produced by dctd_l1_pack from row-major int8.
+ * ===================================================================================== */
+/* bytes of the packed form of n vectors of dimension d */
+size_t dctd_l1_packed_bytes(int64_t n, int32_t d);
+/* d_rows: device int8 [n, d] row-major  ->  d_packed (dctd_l1_packed_bytes(n, d) bytes).
+ * `n_offset` vectors are assumed to be already packed in d_packed (append, as IndexFlat.add). */
+int dctd_l1_pack(const int8_t *d_rows, int64_t n, int32_t d, int64_t n_offset, void *d_packed,
+                 void *stream);
+/* inverse of dctd_l1_pack (used by write_index / reconstruct) */
+int dctd_l1_unpack(const void *d_packed, int64_t n, int32_t d, int8_t *d_rows, void *stream);
+
+size_t dctd_l1_topk_workspace_bytes(int64_t nq, int64_t n, int32_t d, int32_t k);
+/* d_q: device int8 [nq, d] row-major queries.  id_base is added to every reported position
+ * (shard offset).  d_dist float32 [nq, k], d_ids int64 [nq, k]. */
+int dctd_l1_topk(const int8_t *d_q, int64_t nq, const void *d_packed, int64_t n, int32_t d,
+                 int32_t k, int64_t id_base, float *d_dist, int64_t *d_ids, void *d_workspace,
+                 size_t workspace_bytes, void *stream);
+/* k-way merge of `parts` sorted lists: d_dist_parts float32 [parts, nq, k], d_ids_parts int64
+ * [parts, nq, k] (each ascending by (dist, id), padded with (FLT_MAX, -1)) -> [nq, k].
+ * Used after the NCCL all-gather of the per-rank results of a sharded database. */
+int dctd_l1_topk_merge(const float *d_dist_parts, const int64_t *d_ids_parts, int32_t parts,
+                       int64_t nq, int32_t k, float *d_dist, int64_t *d_ids, void *stream);
+
+/* Pairwise scorer of reference src/dct-sim.py:12-50: for pair p, the int L1 distances of every
+ * fingerprint of protein a[p] against every fingerprint of protein b[p] (rows
+ * [off[x], off[x+1]) of d_fps, int8 [n_fps, d] row-major): d_min_dist[p] = min over all
+ * fingerprint pairs, d_last_dist[p] = distance of the last-vs-last pair.  The caller turns them
+ * into similarities (1 - min(dist/17000, 1)) on the host in float64, as the reference does. */
+int dctd_l1_pair_scores(const int8_t *d_fps, int32_t d, const int64_t *d_off, const int32_t *d_pair_a,
+                        const int32_t *d_pair_b, int64_t n_pairs, int32_t *d_min_dist,
+                        int32_t *d_last_dist, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DCTD_H */

@@ -1,0 +1,92 @@
+"""CPU-side checks of the C-ABI library: it loads, exports every symbol include/dctd.h declares,
+and the host-only planner works without a GPU.  No compute calls."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from dctdomain_b200 import _lib
+
+
+@pytest.fixture(scope='module')
+def lib():
+    if not os.path.exists(_lib.LIB_PATH):
+        _lib.build()
+    return _lib.lib()
+
+
+def test_exports_every_declared_symbol(lib):
+    names = _lib.exported_symbols()
+    assert len(names) >= 18
+    for name in names:
+        assert hasattr(lib, name), name
+    assert lib.dctd_version() == 100
+    assert lib.dctd_strerror(-3) == b'workspace too small'
+
+
+def _plan(lib, **kw):
+    from dctdomain_b200.fingerprint import make_plan
+    return make_plan(**kw)
+
+
+def _dump(lib, plan):
+    npc, nit = C.c_int64(), C.c_int64()
+    lib.dctd_fp_plan_dump(plan.handle, None, 0, None, 0, C.byref(npc), C.byref(nit))
+    pieces = np.zeros((npc.value, 6), dtype=np.int32)
+    items = np.zeros((nit.value, 8), dtype=np.int32)
+    lib.dctd_fp_plan_dump(plan.handle, pieces.ctypes.data, npc.value, items.ctypes.data, nit.value, None, None)
+    return pieces, items
+
+
+def test_planner_single_source(lib):
+    plan = _plan(lib, n_layers=2, D=1280, n=3, m=80, src_rows=[300], prot_src0=[0], prot_nsrc=[1],
+                 dom_prot=[0, 0], dom_seg_off=[0, 2, 3], seg_beg=[176, 0, 0], seg_end=[300, 77, 300])
+    pieces, items = _dump(lib, plan)
+    # domain 0 = rows 176..299 then 0..76 (listed order); domain 1 = the whole protein
+    assert pieces.tolist() == [[0, 176, -1, 0, 124, 0], [0, 0, -1, 0, 77, 124], [0, 0, -1, 0, 300, 0]]
+    assert len(items) == 4 and plan.algorithmic_bytes == 2 * (201 + 300) * 1280 * 4
+    assert items[0, 3] - items[0, 2] == 300          # longest first
+
+
+def test_planner_windows_and_split(lib):
+    # L = 1234 -> windows 500, 500, 500, 334 at stride 300; rows [300c, 300c+200) averaged for c >= 1
+    plan = _plan(lib, n_layers=1, D=640, n=3, m=80, src_rows=[500, 500, 500, 334], prot_src0=[0],
+                 prot_nsrc=[4], dom_prot=[0], dom_seg_off=[0, 1], seg_beg=[0], seg_end=[1234])
+    pieces, items = _dump(lib, plan)
+    want = [[0, 0, -1, 0, 300, 0],
+            [0, 300, 1, 0, 200, 300], [1, 200, -1, 0, 100, 500],
+            [1, 300, 2, 0, 200, 600], [2, 200, -1, 0, 100, 800],
+            [2, 300, 3, 0, 200, 900], [3, 200, -1, 0, 134, 1100]]
+    assert pieces.tolist() == want
+    assert len(items) == 3 and sorted((int(a), int(b)) for a, b in items[:, 2:4]) == [(0, 412), (412, 824), (824, 1234)]
+    assert plan.workspace_bytes >= 3 * 2 * 640 * 8
+
+
+def test_planner_rejects_bad_input(lib):
+    with pytest.raises(ValueError):      # domain shorter than n: the reference's reshape fails too
+        _plan(lib, n_layers=1, D=640, n=3, m=80, src_rows=[10], prot_src0=[0], prot_nsrc=[1],
+              dom_prot=[0], dom_seg_off=[0, 1], seg_beg=[0], seg_end=[2])
+    with pytest.raises(ValueError):      # m > D
+        _plan(lib, n_layers=1, D=64, n=3, m=80, src_rows=[10], prot_src0=[0], prot_nsrc=[1],
+              dom_prot=[0], dom_seg_off=[0, 1], seg_beg=[0], seg_end=[10])
+    with pytest.raises(_lib.DctdError):  # stride < overlap: rows would sit in three windows
+        _plan(lib, n_layers=1, D=640, n=3, m=80, src_rows=[300, 300, 250], prot_src0=[0], prot_nsrc=[3],
+              dom_prot=[0], dom_seg_off=[0, 1], seg_beg=[0], seg_end=[300], maxlen=300, overlap=200)
+
+
+def test_parse_domain_matches_reference_quirks():
+    from dctdomain_b200.fingerprint import parse_domain
+    assert parse_domain('300-350,310-320,1-50', 200) == ([(0, 50)], '310-320,1-50')
+    assert parse_domain('50-300', 200) == ([(49, 200)], '50-300')
+    assert parse_domain('500-600', 200) == ([], '')
+    assert parse_domain('177-331,1-77', 400) == ([(176, 331), (0, 77)], '177-331,1-77')
+
+
+def test_no_oracle_import_in_product():
+    root = os.path.dirname(_lib.__file__)
+    for dirpath, _, files in os.walk(root):
+        for f in files:
+            if f.endswith(('.py', '.cu', '.cuh', '.h')):
+                text = open(os.path.join(dirpath, f)).read()
+                assert 'import oracle' not in text and 'from oracle' not in text, f
