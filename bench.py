@@ -1,0 +1,386 @@
+#!/usr/bin/env python
+"""Benchmark of the two DCTdomain hot paths on B200 (contract: see the task statement / DESIGN.md §6).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]          # ours (N > 1: launched by torchrun)
+    python bench.py --impl reference [...]                       # the reference's CPU path (oracle port)
+
+Primary line = BASELINE.json metric part (i), domain fingerprints/s, on configs[1]:
+  100k synthetic domains, L ~ U{40..500}, two ESM-2 layers x 1280 fp32.  A step is one batch of
+  --batch domains (default 4096, ~11 GB of embeddings: far larger than the 126 MB L2); the
+  default 25 steps cover 102,400 domains.  `value` times the kernel path with inputs resident in
+  HBM; `e2e` times the public Python API (`quantize_batch` on Fingerprint objects) with pinned host
+  embeddings, H2D + kernel + D2H inside the timed region.
+The same JSON line carries `search`: part (ii) of the metric, L1 top-50 query.DB pairs/s on a
+1M-fingerprint database (configs[3] size), sharded over the N ranks with an NCCL all-gather merge.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, 'tests')):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+D = 1280
+LAYERS = 2
+QDIM = [3, 80, 3, 80]
+LMIN, LMAX = 40, 500
+
+
+def batch_lengths(seed: int, n: int) -> np.ndarray:
+    return np.random.RandomState(seed).randint(LMIN, LMAX + 1, size=n)
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU reference arm (oracle port of src/fingerprint.py under multiprocessing.Pool, like make_db --cpu N)
+# ------------------------------------------------------------------------------------------------
+_CPU_EMB = None
+
+
+def _cpu_task(i):
+    from oracle import fingerprint_oracle as fo
+    emb = _CPU_EMB[i % len(_CPU_EMB)]
+    L = emb[15].shape[0]
+    q, _ = fo.quantize_faithful(emb, [f'1-{L}'], QDIM)
+    return int(q[f'1-{L}'].sum())
+
+
+def cpu_fingerprint_rate(n_domains: int, cores: int, repeat_pool: int = 64):
+    """domains/s of the faithful oracle port on `cores` processes.  Workers are forked after the
+    inputs exist (no pickling of embeddings, which the reference does pay: make_db.py:48-49)."""
+    import multiprocessing as mp
+    import synth
+    global _CPU_EMB
+    lens = batch_lengths(12345, min(n_domains, repeat_pool))
+    _CPU_EMB = [synth.layers(900 + i, int(L), D, 'white') for i, L in enumerate(lens)]
+    ctx = mp.get_context('fork')
+    with ctx.Pool(cores) as pool:
+        pool.map(_cpu_task, range(cores))                      # warm the workers
+        t0 = time.perf_counter()
+        pool.map(_cpu_task, range(n_domains), chunksize=1)
+        dt = time.perf_counter() - t0
+    return n_domains / dt, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    per_step = max(cores * 16, 64)
+    rates = []
+    for s in range(args.warmup + args.steps):
+        r, dt = cpu_fingerprint_rate(per_step, cores)
+        if s >= args.warmup:
+            rates.append((r, dt))
+    total_t = sum(dt for _, dt in rates)
+    value = per_step * len(rates) / total_t
+    sample = (f'{per_step} domains per step, L~U{{{LMIN}..{LMAX}}}, {LAYERS}x{D} fp32, oracle port of '
+              f'reference fingerprint.py quantize under multiprocessing.Pool({cores})')
+    line = {
+        'impl': 'reference', 'metric': 'domain fingerprints/s', 'value': value, 'unit': 'fingerprints/s',
+        'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': total_t / len(rates) * 1e3,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': {'workload': workload_name(args.batch), 'sample': sample},
+        'cpu_baseline': {'value': value, 'unit': 'fingerprints/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': value, 'unit': 'fingerprints/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_name(batch):
+    return (f'configs[1]: batched fingerprinting of synthetic domains, L~U{{{LMIN}..{LMAX}}}, {LAYERS} ESM-2 layers '
+            f'x {D} fp32, qdim {QDIM}; {batch} domains per step')
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.proc, self.index = None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
+                                          '-lms', '100', '-i', str(self.index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, smax, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for row in out.strip().splitlines():
+            f = [x.strip() for x in row.split(',')]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith('active'):
+                    reasons.add(name)
+        # under load = the upper half of the samples (the sampler also sees the idle edges)
+        load = sorted(sm)[len(sm) // 2:] if sm else []
+        return {'sm_mhz': statistics.median(load) if load else None, 'sm_max_mhz': max(smax) if smax else None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# ours
+# ------------------------------------------------------------------------------------------------
+def peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        return float(json.load(open(path))['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    return 6650.0, 'fallback (B200_PROFILING.md, MEASURED_PEAKS.json absent)'
+
+
+def traffic_for(kernel):
+    path = os.path.join(ROOT, 'profiles', 'roofline_traffic.json')
+    if os.path.exists(path):
+        return json.load(open(path)).get(kernel)
+    return None
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from dctdomain_b200 import _lib
+    from dctdomain_b200 import index as dindex
+    from dctdomain_b200.fingerprint import Fingerprint, execute_plan, make_plan, quantize_batch
+    from dctdomain_b200.sharded import ShardedIndex, shard_bounds
+    import synth
+
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device; there is no CPU fallback (use --impl reference for the CPU arm)')
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    L = _lib.lib()
+    B = args.batch
+    # ---- fingerprint workload: `pool` distinct resident batches (each >> L2), cycled ----
+    pool = []
+    torch.manual_seed(1234 + rank)
+    for b in range(args.pool):
+        lens = batch_lengths(1000 * rank + b, B)
+        off = np.concatenate([[0], np.cumsum(lens)])
+        total = int(off[-1])
+        layers = [torch.randn(total, D, device=dev) for _ in range(LAYERS)]
+        plan = make_plan(LAYERS, D, QDIM[0], QDIM[1], [total], [0], [1], [0] * B, list(range(B + 1)), off[:-1], off[1:])
+        out = torch.empty((B, LAYERS * QDIM[0] * QDIM[1]), dtype=torch.int8, device=dev)
+        ws = torch.empty(max(plan.workspace_bytes, 256), dtype=torch.uint8, device=dev)
+        execute_plan(plan, [[layers[0]], [layers[1]]], out, workspace=ws)        # uploads the plan tables
+        pool.append((plan, layers, out, ws))
+    torch.cuda.synchronize()
+
+    def step(i):
+        plan, layers, out, ws = pool[i % len(pool)]
+        execute_plan(plan, [[layers[0]], [layers[1]]], out, tables_resident=True, workspace=ws)
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    L.dctd_launch_count(1)
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    barrier()
+    evs[0].record()
+    for i in range(args.steps):
+        step(args.warmup + i)
+        evs[i + 1].record()
+    barrier()
+    launches = int(L.dctd_launch_count(0))
+    total_ms = evs[0].elapsed_time(evs[-1])
+    per_step = [evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps)]
+    algo = [pool[(args.warmup + i) % len(pool)][0].algorithmic_bytes for i in range(args.steps)]
+    total_ms = max_over_ranks(total_ms)
+    clocks = sampler.stop() if rank == 0 else None
+    value = B * args.steps * world / (total_ms * 1e-3)
+    peak, peak_src = peaks()
+    achieved = sum(algo) / (sum(per_step) * 1e-3) / 1e9
+    roofline = {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+                'traffic': traffic_for('fp_kernel'), 'kernel': 'fp_kernel<K=2,VEC=4> (csrc/fingerprint.cu)',
+                'algorithmic_bytes_per_launch': sum(algo) / len(algo), 'avg_launch_ms': sum(per_step) / len(per_step),
+                'peak_source': peak_src}
+
+    # ---- e2e: public API, pinned host embeddings -> int8 fingerprints on the host ----
+    Be = args.e2e_batch
+    elens = batch_lengths(777 + rank, Be)
+    host_fps = []
+    gen = torch.Generator().manual_seed(99 + rank)
+    for i, Ln in enumerate(elens):
+        emb = {15: torch.randn(int(Ln), D, generator=gen).pin_memory(), 21: torch.randn(int(Ln), D, generator=gen).pin_memory()}
+        host_fps.append((f'p{i}', int(Ln), emb))
+    h2d = int(sum(2 * int(Ln) * D * 4 for Ln in elens))
+    d2h = Be * LAYERS * QDIM[0] * QDIM[1]
+
+    def e2e_step():
+        fps = [Fingerprint(pid=pid, seq='', embed=emb, domains=[f'1-{Ln}'], quants={}) for pid, Ln, emb in host_fps]
+        quantize_batch(fps, QDIM, device=dev)
+        return fps
+
+    e2e_steps = max(3, min(args.steps, 8))
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        fps = e2e_step()
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e = {'value': Be * e2e_steps * world / e2e_s, 'unit': 'fingerprints/s', 'h2d_bytes_per_step': h2d,
+           'd2h_bytes_per_step': d2h, 'steps': e2e_steps, 'domains_per_step': Be,
+           'api': 'dctdomain_b200.fingerprint.quantize_batch(list[Fingerprint]) with pinned host embeddings'}
+
+    # ---- search: part (ii) of the metric ----
+    search = None
+    if not args.no_search:
+        search = run_search(args, dev, rank, world, dist, torch, dindex, ShardedIndex, shard_bounds, synth, barrier,
+                            max_over_ranks, L, peak)
+
+    # ---- CPU baseline (rank 0, N = 1 only) ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cores = os.cpu_count() or 1
+        n = max(cores * 6, 48)
+        r, dt = cpu_fingerprint_rate(n, cores)
+        cpu = {'value': r, 'unit': 'fingerprints/s', 'cores': cores, 'kind': 'port', 'seconds': dt,
+               'sample': f'{n} domains, L~U{{{LMIN}..{LMAX}}}, {LAYERS}x{D} fp32: oracle port of reference '
+                         f'fingerprint.py quantize under multiprocessing.Pool({cores}) (embeddings pre-forked, not pickled)'}
+
+    if rank == 0:
+        line = {
+            'metric': 'domain fingerprints/s', 'value': value, 'unit': 'fingerprints/s', 'n_gpus': world,
+            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': total_ms / args.steps,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': workload_name(B), 'domains_per_step': B, 'resident_batches': len(pool),
+                       'l2': 'inputs larger than L2 (each step streams ~%.1f GB)' % (sum(algo) / len(algo) / 1e9),
+                       'parallelism': f'domains sharded over {world} rank(s), no collective'},
+            'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches, 'roofline': roofline, 'cpu_baseline': cpu,
+            'search': search,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_search(args, dev, rank, world, dist, torch, dindex, ShardedIndex, shard_bounds, synth, barrier,
+               max_over_ranks, L, peak):
+    n_db, nq, k = args.search_db, args.search_queries, 50
+    b, e = shard_bounds(n_db, world, rank)
+    # synthetic fingerprints generated on the device per shard (values 0..127, like real ones)
+    g = torch.Generator(device=dev).manual_seed(4242 + rank)
+    shard = torch.clamp(torch.randn((e - b, 480), generator=g, device=dev) * 27.7 + 63.6, 0, 127).round().to(torch.int8)
+    sh = ShardedIndex(480, n_db, rank=rank, world=world, device=dev)
+    sh.index.add(shard)
+    # queries: perturbed rows of rank 0's shard, replicated
+    gq = torch.Generator(device=dev).manual_seed(7)
+    if rank == 0:
+        rows = torch.randint(0, e - b, (nq,), generator=gq, device=dev)
+        q = torch.clamp(shard[rows].to(torch.int16) + torch.randint(-3, 4, (nq, 480), generator=gq, device=dev).to(torch.int16),
+                        0, 127).to(torch.int8)
+    else:
+        q = torch.empty((nq, 480), dtype=torch.int8, device=dev)
+    if world > 1:
+        dist.broadcast(q, 0)
+    steps = max(2, min(args.steps, 5))
+    for _ in range(3):
+        sh.search(q, k)
+    barrier()
+    L.dctd_launch_count(1)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(steps):
+        dd, ii = sh.search(q, k)
+    ev1.record()
+    barrier()
+    ms = max_over_ranks(ev0.elapsed_time(ev1))
+    launches = int(L.dctd_launch_count(0))
+    pairs = float(nq) * n_db * steps
+    # e2e: host queries in, host results out (faiss-style index.search), single rank semantics
+    qh = q.cpu().numpy()
+    t0 = time.perf_counter()
+    if world == 1:
+        for _ in range(steps):
+            sh.index.search(qh, k)
+        torch.cuda.synchronize()
+        e2e_pairs = pairs / (time.perf_counter() - t0)
+    else:
+        e2e_pairs = None
+    db_bytes = (e - b) * 480
+    return {'metric': 'L1 top-50 query.DB pairs/s', 'value': pairs / (ms * 1e-3), 'unit': 'pairs/s', 'ms_per_step': ms / steps,
+            'steps': steps, 'scaling': 'strong', 'dtype': 'u8', 'gpu_launches': launches,
+            'config': {'workload': f'configs[3]-sized: {nq} queries x {n_db} int8[480] fingerprints, k=50, DB sharded '
+                                   f'over {world} rank(s), NCCL all-gather merge', 'n_db': n_db, 'nq': nq, 'k': k},
+            'e2e_pairs_per_s': e2e_pairs,
+            'hbm_frac_of_db_stream': (db_bytes / (ms / steps * 1e-3) / 1e9) / peak,
+            'sad4_per_s': pairs * 120 / (ms * 1e-3)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=25)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--batch', type=int, default=4096, help='domains per step')
+    ap.add_argument('--pool', type=int, default=3, help='distinct resident batches cycled through')
+    ap.add_argument('--e2e-batch', type=int, default=512)
+    ap.add_argument('--search-db', type=int, default=1_000_000)
+    ap.add_argument('--search-queries', type=int, default=8192)
+    ap.add_argument('--no-search', action='store_true')
+    ap.add_argument('--no-cpu', action='store_true')
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -9,6 +9,17 @@
 Everything numeric runs in libdctd.so (hand-written CUDA, C ABI in include/dctd.h); there is no
 CPU fallback.
 """
+import sys
+
 from . import _lib  # noqa: F401
 
-__all__ = ['_lib']
+
+def install_faiss_shim():
+    """Registers dctdomain_b200.index as ``faiss`` so that the reference's ``import faiss``
+    (src/database.py:8, src/query_db.py:8) binds to the GPU index without editing those files."""
+    from . import index
+    sys.modules['faiss'] = index
+    return index
+
+
+__all__ = ['_lib', 'install_faiss_shim']

@@ -31,7 +31,7 @@
 namespace {
 
 constexpr int kWarps = 8;            // warps per CTA of the scan kernel
-constexpr int kTD = 4;               // database groups (of 32 vectors) per shared-memory stage
+constexpr int kTDmax = 4;            // database groups (of 32 vectors) per shared-memory stage (1 for wide d)
 constexpr int kStages = 2;
 constexpr int kIdBits = 40;          // key = dist << 40 | position
 constexpr unsigned long long kKeyMax = ~0ULL;
@@ -169,7 +169,7 @@ struct ScanParams {
     long long n_groups, groups_per_split;
 };
 
-template <int TQ>
+template <int TQ, int kTD>
 __global__ void __launch_bounds__(kWarps * 32, 1) l1_scan_kernel(const ScanParams p) {
     constexpr int QT = kWarps * TQ;
     extern __shared__ __align__(128) unsigned char smem[];
@@ -367,28 +367,32 @@ __global__ void pair_scores_kernel(const int8_t *__restrict__ fps, int d, const 
 // host-side configuration shared by workspace_bytes and topk
 // ------------------------------------------------------------------------------------------
 struct ScanConfig {
-    int tq, cap;
+    int tq, td, cap;
     long long n_qtiles, n_groups, splits, groups_per_split;
     size_t smem;
 };
 
 bool make_config(long long nq, long long n, int d, int k, ScanConfig *cfg) {
-    if (k < 1 || k > 992 || d < 1 || d > 4096) return false;
+    if (k < 1 || k > 992 || d < 1 || d > 2048) return false;
     int cap = 128, tq = 8;
     if (k > 96) { cap = 256; tq = 4; }
     if (k > 224) { cap = 512; tq = 2; }
     if (k > 480) { cap = 1024; tq = 1; }
     while (tq > 1 && (long long)kWarps * (tq / 2) >= nq) tq /= 2;   // few queries: smaller tiles
     const int dpad = chunks_of(d) * 16;
-    auto smem_of = [&](int tq_) {
+    int td = kTDmax;
+    auto smem_of = [&](int tq_, int td_) {
         const size_t qt = (size_t)kWarps * tq_;
-        return (size_t)128 + qt * dpad + (size_t)kStages * kTD * 32 * dpad + qt * cap * 8 + qt * 12 + 64;
+        return (size_t)128 + qt * dpad + (size_t)kStages * td_ * 32 * dpad + qt * cap * 8 + qt * 12 + 64;
     };
-    while (tq > 1 && smem_of(tq) > 227 * 1024) tq /= 2;
-    if (smem_of(tq) > 227 * 1024) return false;
+    if (smem_of(1, td) > 227 * 1024) td = 1;            // wide vectors: one group per stage
+    while (tq > 1 && smem_of(tq, td) > 227 * 1024) tq /= 2;
+    if (smem_of(tq, td) > 227 * 1024) return false;
+    const int kTD = td;
     cfg->tq = tq;
+    cfg->td = td;
     cfg->cap = cap;
-    cfg->smem = smem_of(tq);
+    cfg->smem = smem_of(tq, td);
     cfg->n_qtiles = (nq + (long long)kWarps * tq - 1) / ((long long)kWarps * tq);
     cfg->n_groups = (n + 31) / 32;
     const long long tiles = (cfg->n_groups + kTD - 1) / kTD;
@@ -477,11 +481,20 @@ int dctd_l1_topk(const int8_t *d_q, int64_t nq, const void *d_packed, int64_t n,
         if (cfg.n_qtiles > 65535) return DCTD_ERR_UNSUPPORTED;   // caller batches queries
         dim3 grid((unsigned)cfg.splits, (unsigned)cfg.n_qtiles);
         void (*fn)(const ScanParams) = nullptr;
-        switch (cfg.tq) {
-            case 1: fn = l1_scan_kernel<1>; break;
-            case 2: fn = l1_scan_kernel<2>; break;
-            case 4: fn = l1_scan_kernel<4>; break;
-            default: fn = l1_scan_kernel<8>; break;
+        if (cfg.td == kTDmax) {
+            switch (cfg.tq) {
+                case 1: fn = l1_scan_kernel<1, kTDmax>; break;
+                case 2: fn = l1_scan_kernel<2, kTDmax>; break;
+                case 4: fn = l1_scan_kernel<4, kTDmax>; break;
+                default: fn = l1_scan_kernel<8, kTDmax>; break;
+            }
+        } else {
+            switch (cfg.tq) {
+                case 1: fn = l1_scan_kernel<1, 1>; break;
+                case 2: fn = l1_scan_kernel<2, 1>; break;
+                case 4: fn = l1_scan_kernel<4, 1>; break;
+                default: fn = l1_scan_kernel<8, 1>; break;
+            }
         }
         DCTD_CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem));
         fn<<<grid, kWarps * 32, cfg.smem, stream>>>(sp);

@@ -1,0 +1,185 @@
+"""Drop-in for the faiss objects the reference uses on its search path.
+
+Reference call sites:
+    index = faiss.IndexFlatL2(d); index.add(fps); faiss.write_index(index, path)   src/database.py:241-243
+    index = faiss.read_index(path); index.metric_type = faiss.METRIC_L1            src/query_db.py:75-76
+    dm, im = index.search(que_arr, k)                                              src/query_db.py:87
+so ``import dctdomain_b200.index as faiss`` keeps those lines unchanged.  The database is held on
+the GPU as packed int8 (csrc/l1topk.cu); ``search`` is exhaustive L1 top-k with faiss' result
+convention: float32 distances, int64 positions, k smallest by (distance, position) ascending,
+(FLT_MAX, -1) padding.
+
+Only the L1 metric is implemented (the reference never searches with anything else: it flips
+``metric_type`` to METRIC_L1 right after ``read_index``); ``search`` with another metric raises.
+Vectors must be integer valued in [-128, 127] - DCT fingerprints are int8 by construction
+(src/database.py:240) - anything else raises instead of being rounded silently.
+"""
+from __future__ import annotations
+
+import struct
+
+import numpy as np
+import torch
+
+from . import _lib
+from .fingerprint import _device, _workspace
+
+# faiss MetricType values
+METRIC_INNER_PRODUCT = 0
+METRIC_L2 = 1
+METRIC_L1 = 2
+
+FLT_MAX = float(np.finfo(np.float32).max)
+_QUERY_BATCH = 32768
+
+
+def _as_int8(x, d=None) -> np.ndarray:
+    a = np.asarray(x)
+    if a.ndim != 2:
+        raise ValueError('expected a [n, d] array')
+    if d is not None and a.shape[1] != d:
+        raise ValueError(f'vector dimension {a.shape[1]} != index dimension {d}')
+    if a.dtype == np.int8:
+        return np.ascontiguousarray(a)
+    r = np.rint(a)
+    if a.size and (not np.array_equal(r, a) or r.min() < -128 or r.max() > 127):
+        raise ValueError('dctdomain_b200.index stores int8 fingerprints: values must be integers in [-128, 127]')
+    return np.ascontiguousarray(r.astype(np.int8))
+
+
+class IndexFlat:
+    """Exhaustive index over int8 vectors resident on one GPU."""
+
+    def __init__(self, d: int, metric: int = METRIC_L2, device=None):
+        self.d = int(d)
+        self.metric_type = metric
+        self.is_trained = True
+        self.ntotal = 0
+        self._dev = _device(device)
+        self._packed = None       # torch.uint8 device buffer in dctd_l1_pack layout
+        self._cap = 0
+
+    # -- storage --------------------------------------------------------------------------
+    def _reserve(self, n: int):
+        if n <= self._cap:
+            return
+        cap = max(n, int(self._cap * 1.5), 1024)
+        nbytes = int(_lib.lib().dctd_l1_packed_bytes(cap, self.d))
+        buf = torch.empty(nbytes, dtype=torch.uint8, device=self._dev)
+        if self._packed is not None and self.ntotal:
+            used = int(_lib.lib().dctd_l1_packed_bytes(self.ntotal, self.d))
+            buf[:used].copy_(self._packed[:used])
+        self._packed, self._cap = buf, cap
+
+    def add(self, x):
+        """Append vectors (faiss IndexFlat.add).  ``x``: [n, d] numpy array or int8 CUDA tensor."""
+        if isinstance(x, torch.Tensor) and x.is_cuda:
+            if x.dtype != torch.int8 or x.dim() != 2 or x.shape[1] != self.d:
+                raise ValueError('CUDA input must be an int8 [n, d] tensor')
+            rows = x.contiguous()
+        else:
+            rows = torch.from_numpy(_as_int8(x, self.d)).to(self._dev)
+        n = int(rows.shape[0])
+        if n == 0:
+            return
+        self._reserve(self.ntotal + n)
+        with torch.cuda.device(self._dev):
+            rc = _lib.lib().dctd_l1_pack(rows.data_ptr(), n, self.d, self.ntotal, self._packed.data_ptr(),
+                                         torch.cuda.current_stream(self._dev).cuda_stream)
+        _lib.check(rc, 'dctd_l1_pack')
+        self.ntotal += n
+
+    def reconstruct_n(self, i0: int = 0, n: int = -1) -> np.ndarray:
+        """Stored vectors as int8 [n, d] (row-major)."""
+        if n < 0:
+            n = self.ntotal - i0
+        out = torch.empty((self.ntotal, self.d), dtype=torch.int8, device=self._dev)
+        if self.ntotal:
+            with torch.cuda.device(self._dev):
+                rc = _lib.lib().dctd_l1_unpack(self._packed.data_ptr(), self.ntotal, self.d, out.data_ptr(),
+                                               torch.cuda.current_stream(self._dev).cuda_stream)
+            _lib.check(rc, 'dctd_l1_unpack')
+        return out[i0:i0 + n].cpu().numpy()
+
+    # -- search ---------------------------------------------------------------------------
+    def search_device(self, q: torch.Tensor, k: int, id_base: int = 0):
+        """int8 CUDA queries [nq, d] -> (float32 [nq, k], int64 [nq, k]) CUDA tensors, stream ordered."""
+        if self.metric_type != METRIC_L1:
+            raise NotImplementedError('only METRIC_L1 search is implemented (set index.metric_type = METRIC_L1, '
+                                      'as reference src/query_db.py:76 does)')
+        if q.dtype != torch.int8 or q.dim() != 2 or q.shape[1] != self.d or not q.is_cuda:
+            raise ValueError('queries must be an int8 CUDA tensor [nq, d]')
+        if k < 1:
+            raise ValueError('k must be >= 1')
+        L = _lib.lib()
+        q = q.contiguous()
+        nq = int(q.shape[0])
+        dist = torch.empty((nq, k), dtype=torch.float32, device=self._dev)
+        ids = torch.empty((nq, k), dtype=torch.int64, device=self._dev)
+        packed_ptr = self._packed.data_ptr() if self._packed is not None else 0
+        with torch.cuda.device(self._dev):
+            stream = torch.cuda.current_stream(self._dev).cuda_stream
+            for b in range(0, nq, _QUERY_BATCH):
+                e = min(nq, b + _QUERY_BATCH)
+                need = int(L.dctd_l1_topk_workspace_bytes(e - b, self.ntotal, self.d, k))
+                if need == 0:
+                    raise _lib.DctdError(_lib.ERR_UNSUPPORTED, f'k={k}, d={self.d} not supported (k <= 992, d <= 2048)')
+                ws = _workspace(self._dev, need)
+                rc = L.dctd_l1_topk(q[b:e].data_ptr(), e - b, packed_ptr, self.ntotal, self.d, k, id_base,
+                                    dist[b:e].data_ptr(), ids[b:e].data_ptr(), ws.data_ptr(), ws.numel(), stream)
+                _lib.check(rc, 'dctd_l1_topk')
+        return dist, ids
+
+    def search(self, x, k: int):
+        """faiss-style ``D, I = index.search(x, k)`` with host arrays."""
+        q = torch.from_numpy(_as_int8(x, self.d)).to(self._dev)
+        dist, ids = self.search_device(q, int(k))
+        return dist.cpu().numpy(), ids.cpu().numpy()
+
+
+class IndexFlatL2(IndexFlat):
+    def __init__(self, d: int, device=None):
+        super().__init__(d, METRIC_L2, device)
+
+
+class IndexFlatL1(IndexFlat):
+    def __init__(self, d: int, device=None):
+        super().__init__(d, METRIC_L1, device)
+
+
+# ------------------------------------------------------------------------------------------
+# .index files, faiss IndexFlat layout:
+#   fourcc "IxF2" | d int32 | ntotal int64 | 2 x int64 dummy (1 << 20) | is_trained u8 |
+#   metric_type int32 | n_floats uint64 | float32 data
+# ------------------------------------------------------------------------------------------
+_FOURCC = {METRIC_L2: b'IxF2', METRIC_INNER_PRODUCT: b'IxFI'}
+
+
+def write_index(index: IndexFlat, path: str):
+    """faiss.write_index for a flat index.  The file always records the metric the index was built
+    with (the reference builds IndexFlatL2 and flips to L1 only in memory, src/query_db.py:76)."""
+    metric = index.metric_type if index.metric_type in _FOURCC else METRIC_L2
+    data = index.reconstruct_n().astype(np.float32)
+    with open(path, 'wb') as f:
+        f.write(_FOURCC[metric])
+        f.write(struct.pack('<iqqqBi', index.d, index.ntotal, 1 << 20, 1 << 20, 1, metric))
+        f.write(struct.pack('<Q', index.ntotal * index.d))
+        f.write(data.tobytes())
+
+
+def read_index(path: str, device=None) -> IndexFlat:
+    """faiss.read_index for a flat index file (written by faiss or by write_index above)."""
+    with open(path, 'rb') as f:
+        fourcc = f.read(4)
+        if fourcc not in (b'IxF2', b'IxFI', b'IxFl'):
+            raise ValueError(f'{path}: not a flat faiss index (fourcc {fourcc!r})')
+        d, ntotal, _, _, _trained, metric = struct.unpack('<iqqqBi', f.read(4 + 8 * 3 + 1 + 4))
+        if metric > 1:
+            f.read(4)                       # metric_arg
+        (n_floats,) = struct.unpack('<Q', f.read(8))
+        if n_floats != ntotal * d:
+            raise ValueError(f'{path}: inconsistent header ({n_floats} floats for {ntotal} x {d})')
+        data = np.frombuffer(f.read(n_floats * 4), dtype='<f4').reshape(ntotal, d)
+    index = IndexFlat(d, metric, device)
+    index.add(data)
+    return index

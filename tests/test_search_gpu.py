@@ -1,0 +1,202 @@
+"""Parity of the CUDA search path (through the C ABI) with the CPU oracle and the reference's shipped
+fixtures.  Integer work: everything here is bit exact, including hit order with ties by index."""
+import argparse
+import logging
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import synth
+from minidb import MiniDB
+from oracle import search_oracle as so
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+
+
+def _index(db, metric_l1=True, pieces=1):
+    from dctdomain_b200 import index as dindex
+    idx = dindex.IndexFlatL2(db.shape[1])
+    for part in np.array_split(db, pieces):
+        idx.add(part)
+    if metric_l1:
+        idx.metric_type = dindex.METRIC_L1
+    return idx
+
+
+def _check(q, db, k, pieces=1):
+    dm, im = _index(db, pieces=pieces).search(q, k)
+    dm2, im2 = so.l1_topk(q, db, k, threads=4)
+    assert dm.dtype == np.float32 and im.dtype == np.int64 and dm.shape == (len(q), k)
+    assert np.array_equal(im, im2), np.argwhere(im != im2)[:5]
+    assert np.array_equal(dm, dm2)
+
+
+def test_example_fixture_all_vs_all():
+    z = np.load(os.path.join(G, 'example-dct.npz'))
+    _check(z['dct'], z['dct'], 50)          # N = 43 < k: (-1, FLT_MAX) padding
+    _check(z['dct'], z['dct'], 5)
+
+
+@pytest.mark.parametrize('n', [1, 31, 32, 33, 129, 5000])
+@pytest.mark.parametrize('k', [1, 50, 100])
+def test_sizes(n, k):
+    db = synth.fingerprints(n, n)
+    q = synth.fingerprints(n + 1, 13)
+    _check(q, db, k)
+
+
+@pytest.mark.parametrize('k', [7, 96, 97, 224, 225, 300, 480, 481, 992])
+def test_k_range(k):
+    db = synth.fingerprints(3, 3000)
+    _check(db[:9], db, k)
+
+
+@pytest.mark.parametrize('nq', [1, 8, 9, 64, 65, 1000])
+def test_query_counts(nq):
+    db = synth.fingerprints(5, 20000)
+    q = np.concatenate([db[:nq // 2], synth.fingerprints(6, nq - nq // 2)])
+    _check(q, db, 50)
+
+
+def test_boundary_ties_and_duplicates():
+    rs = np.random.RandomState(0)
+    db = rs.randint(0, 3, size=(4000, 480)).astype(np.int8)        # tiny alphabet: massive distance ties
+    db[100:140] = db[7]                                            # exact duplicates of one vector
+    db[3000:3100] = db[7]
+    _check(db[:40], db, 50)
+    _check(db[:40], db, 10)
+    same = np.tile(synth.fingerprints(1, 1), (2000, 1))            # every distance equal: ids 0..k-1 win
+    dm, im = _index(same).search(same[:3], 50)
+    assert (im == np.arange(50)[None, :]).all() and (dm == 0).all()
+
+
+def test_negative_values_and_other_dims():
+    rs = np.random.RandomState(1)
+    for d in (16, 100, 480, 481, 1024):
+        db = rs.randint(-128, 128, size=(1500, d)).astype(np.int8)
+        _check(db[:20], db, 20)
+
+
+def test_add_in_pieces_and_roundtrip(tmp_path):
+    from dctdomain_b200 import index as dindex
+    db = synth.fingerprints(9, 1000)
+    idx = _index(db, pieces=7)
+    assert idx.ntotal == 1000 and np.array_equal(idx.reconstruct_n(), db)
+    _check(db[:30], db, 50, pieces=7)
+    path = str(tmp_path / 'x.index')
+    dindex.write_index(idx, path)
+    raw = open(path, 'rb').read()
+    assert raw[:4] == b'IxF2' and len(raw) == 4 + 4 + 8 * 3 + 1 + 4 + 8 + 1000 * 480 * 4
+    back = dindex.read_index(path)
+    assert back.ntotal == 1000 and back.d == 480 and back.metric_type == dindex.METRIC_L2
+    with pytest.raises(NotImplementedError):
+        back.search(db[:2], 5)                 # like the reference, the caller must flip to METRIC_L1
+    back.metric_type = dindex.METRIC_L1
+    dm, im = back.search(db[:30], 50)
+    dm2, im2 = so.l1_topk(db[:30], db, 50)
+    assert np.array_equal(im, im2) and np.array_equal(dm, dm2)
+    with pytest.raises(ValueError):
+        idx.add(np.full((1, 480), 0.5))        # not int8 valued
+
+
+def test_empty_database_and_empty_queries():
+    from dctdomain_b200 import index as dindex
+    idx = dindex.IndexFlatL1(480)
+    dm, im = idx.search(synth.fingerprints(0, 3), 5)
+    assert (im == -1).all() and (dm == np.finfo(np.float32).max).all()
+    idx.add(synth.fingerprints(0, 10))
+    dm, im = idx.search(np.zeros((0, 480), dtype=np.int8), 5)
+    assert dm.shape == (0, 5)
+
+
+def test_merge_of_sharded_results_equals_whole():
+    """What the multi-GPU path does: contiguous shards, per-shard top-k with id_base, k-way merge."""
+    from dctdomain_b200 import _lib
+    db = synth.fingerprints(21, 10000)
+    db[5000:5050] = db[3]                      # ties across shard boundaries
+    q = torch.from_numpy(db[:100]).cuda()
+    k, parts = 50, 4
+    dists, ids = [], []
+    bounds = np.linspace(0, len(db), parts + 1).astype(int)
+    for s in range(parts):
+        idx = _index(db[bounds[s]:bounds[s + 1]])
+        d_, i_ = idx.search_device(q, k, id_base=int(bounds[s]))
+        dists.append(d_)
+        ids.append(i_)
+    dp, ip = torch.stack(dists).contiguous(), torch.stack(ids).contiguous()
+    out_d = torch.empty((100, k), dtype=torch.float32, device='cuda')
+    out_i = torch.empty((100, k), dtype=torch.int64, device='cuda')
+    rc = _lib.lib().dctd_l1_topk_merge(dp.data_ptr(), ip.data_ptr(), parts, 100, k, out_d.data_ptr(),
+                                       out_i.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    _lib.check(rc)
+    dm2, im2 = so.l1_topk(db[:100], db, k, threads=4)
+    assert np.array_equal(out_i.cpu().numpy(), im2) and np.array_equal(out_d.cpu().numpy(), dm2)
+
+
+def test_search_db_reproduces_example_search_txt(tmp_path, caplog):
+    """reference test/test/example-search.txt = query_db.py --khits 50 of the example db against itself."""
+    from dctdomain_b200 import query_db as dq
+    z = np.load(os.path.join(G, 'example-dct.npz'))
+    dbp = str(tmp_path / 'example.db')
+    MiniDB(dbp, z).close()
+    idx = _index(z['dct'], metric_l1=False)
+    with caplog.at_level(logging.INFO):
+        dq.search_db(argparse.Namespace(khits=50), MiniDB(dbp), MiniDB(dbp), index=idx)
+    lines = [r.getMessage() for r in caplog.records if r.getMessage().startswith('Query:')]
+    assert lines == open(os.path.join(G, 'example-search.txt')).read().splitlines()
+
+
+def test_dct_sim_pair_reproduces_g6pd(tmp_path):
+    """reference bench/G6PD/G6PD-dctsim.txt = dct-sim.py --dct G6PD-dct.npz --pair G6PD.pair."""
+    from dctdomain_b200 import dct_sim
+    out = str(tmp_path / 'sim.txt')
+    dct_sim.main(['--dct', os.path.join(G, 'G6PD-dct.npz'), '--pair', os.path.join(G, 'G6PD.pair'), '--output', out])
+    assert open(out).read() == open(os.path.join(G, 'G6PD-dctsim.txt')).read()
+    z = np.load(os.path.join(G, 'G6PD-dct.npz'))
+    a, b = z['dct'][z['idx'][0]:z['idx'][1]], z['dct'][z['idx'][1]:z['idx'][2]]
+    assert dct_sim.domain_sim(a, b) == so.domain_sim(a, b)
+    assert dct_sim.prostSimilarity(a[0], b[0]) == so.prost_similarity(a[0], b[0])
+
+
+def test_dct_sim_db_and_all(tmp_path, capsys):
+    from dctdomain_b200 import dct_sim
+    npz = os.path.join(G, 'example-dct.npz')
+    z = np.load(npz)
+    blocks = [z['dct'][z['idx'][i]:z['idx'][i + 1]] for i in range(len(z['sid']))]
+    out = str(tmp_path / 'all.txt')
+    dct_sim.main(['--dct', npz, '--output', out])
+    want = ['#prot1 prot2 sim-domain sim-global']
+    for i in range(len(blocks) - 1):
+        for j in range(i + 1, len(blocks)):
+            mx, s = so.domain_sim(blocks[i], blocks[j])
+            want.append(f"{z['sid'][i]} {z['sid'][j]} {mx:.3f} {s:.3f}")
+    assert open(out).read().splitlines() == want
+    out = str(tmp_path / 'db.txt')
+    dct_sim.main(['--dct', npz, '--db', npz, '--top', '3', '--threshold', '0.3', '--output', out])
+    got = open(out).read().splitlines()
+    assert got[0].startswith('#') and got[1].split()[0] == got[1].split()[1] and got[1].split()[3] == '1.0'
+
+
+def test_properties_at_scale():
+    """1M-vector database (configs[3] size): the oracle is too slow here, so check properties - every
+    query that is a database row finds itself at distance 0 first, distances ascend, ids are unique, and
+    a torch brute force over the same int8 data agrees on a sample."""
+    db = synth.fingerprints(33, 1_000_000)
+    idx = _index(db)
+    rs = np.random.RandomState(2)
+    rows = rs.choice(len(db), size=256, replace=False)
+    dm, im = idx.search(db[rows], 50)
+    assert (dm[:, 0] == 0).all() and (np.diff(dm, axis=1) >= 0).all()
+    assert all(len(set(r)) == 50 for r in im)
+    first = im[:, 0]
+    assert all(np.array_equal(db[f], db[r]) for f, r in zip(first, rows))
+    dbt = torch.from_numpy(db).cuda()
+    for qi in range(8):
+        dist = (dbt.to(torch.int16) - dbt[rows[qi]].to(torch.int16)).abs().sum(dim=1, dtype=torch.int32)
+        key = dist.to(torch.int64) * (1 << 32) + torch.arange(len(db), device='cuda')
+        best = torch.sort(key)[0][:50]
+        assert np.array_equal((best % (1 << 32)).cpu().numpy(), im[qi])
+        assert np.array_equal((best // (1 << 32)).cpu().numpy().astype(np.float32), dm[qi])
