@@ -64,12 +64,14 @@ struct Layout {             // thread / shared-memory layout derived from (D, n,
     int CT;                 // column tiles per thread
     int RL;                 // row lanes (threads sharing a column group, interleaved rows)
     int T;                  // threads per CTA
+    int table_len;          // entries of the extended pass-2a cosine table: 4D + 8m
     size_t smem;            // dynamic shared memory bytes
     size_t off_t4d, off_y, off_cb, off_scr, off_tm, off_mj;
 };
 
 struct Params {
     const float *const *src;
+    const float *table;     // extended cosine table in the workspace (fp_table_kernel)
     const Piece *pieces;
     const DomInfo *doms;
     const Item *items;
@@ -93,7 +95,7 @@ struct dctd_fp_plan {
     int64_t n_slabs;          // partial-sum slabs of (n-1)*D doubles
     int64_t algo_bytes;
     // device blob layout (bytes from the workspace base)
-    size_t off_pieces, off_doms, off_items, off_src, off_counters, off_partials, total;
+    size_t off_pieces, off_doms, off_items, off_src, off_counters, off_table, off_partials, total;
     void *blob;               // host copy of [pieces | doms | items], pinned when possible
     bool blob_pinned;
     size_t blob_bytes;
@@ -104,124 +106,209 @@ namespace {
 // ------------------------------------------------------------------------------------------
 // device helpers
 // ------------------------------------------------------------------------------------------
-template <int VEC>
-struct Vec;
-template <>
-struct Vec<4> {
-    float v[4];
-    __device__ __forceinline__ static Vec load(const float *p) {
-        Vec r;
-        // streaming read: data is used exactly once, keep it out of L1
-        asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
-                     : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3])
-                     : "l"(p));
-        return r;
-    }
-};
-template <>
-struct Vec<1> {
-    float v[1];
-    __device__ __forceinline__ static Vec load(const float *p) {
-        Vec r;
-        asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r.v[0]) : "l"(p));
-        return r;
-    }
-};
-
-template <int VEC>
-__device__ __forceinline__ Vec<VEC> zero_vec() {
-    Vec<VEC> r;
-#pragma unroll
-    for (int i = 0; i < VEC; ++i) r.v[i] = 0.f;
+// packed pair of floats (sm_100 FADD2 / FMUL2 / FFMA2: two IEEE fp32 ops per instruction)
+typedef unsigned long long pk2;
+__device__ __forceinline__ pk2 pk(float lo, float hi) {
+    pk2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpk(pk2 v, float &lo, float &hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ pk2 add2(pk2 a, pk2 b) {
+    pk2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ pk2 mul2(pk2 a, pk2 b) {
+    pk2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ pk2 fma2(pk2 a, pk2 b, pk2 c) {
+    pk2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
     return r;
 }
 
-// one row of the domain at this thread's columns: single source or the overlap average
-template <int VEC, bool DUAL>
-__device__ __forceinline__ Vec<VEC> load_row(const float *pa, const float *pb) {
-    Vec<VEC> a = Vec<VEC>::load(pa);
-    if (DUAL) {
-        Vec<VEC> b = Vec<VEC>::load(pb);
-#pragma unroll
-        for (int i = 0; i < VEC; ++i) a.v[i] = (a.v[i] + b.v[i]) * 0.5f;   // embedding.py:186
-    }
-    return a;
+// streaming 16-byte read (data is used exactly once: keep it out of L1), as two packed pairs
+__device__ __forceinline__ void ldg_stream4(const float *p, pk2 &lo, pk2 &hi) {
+    asm volatile("ld.global.nc.L1::no_allocate.v2.b64 {%0,%1}, [%2];" : "=l"(lo), "=l"(hi) : "l"(p));
+}
+__device__ __forceinline__ float ldg_stream1(const float *p) {
+    float r;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
+    return r;
 }
 
-// Streams rows [0, nr) of one piece (this thread: rows rl, rl+RL, ...), accumulating
-// acc[k][v] += (x - pivot) * cb[row][k].
-template <int K, int VEC, int U, bool DUAL>
-__device__ __forceinline__ void stream_piece(const float *pa, const float *pb, int64_t ld, int nr,
-                                             int rl, int RL, const float *cb,
-                                             const float (&piv)[VEC], double (&acc)[K][VEC]) {
-    int i = rl;
+// ---- pass 1, float4 path: rows rl, rl+RL, ... of one piece; acc[k] += (x - pivot) * c_k[row] ----
+// cb2[row*K + k] holds (c, c) so that one FFMA2 covers two columns.
+template <int K, int U, bool DUAL>
+__device__ __forceinline__ void stream_piece4(const float *pa, const float *pb, int64_t ld, int nr, int rl,
+                                              int RL, const pk2 *cb2, pk2 npiv0, pk2 npiv1,
+                                              double (&acc)[K][4]) {
     const int64_t step = (int64_t)RL * ld;
+    const pk2 half = pk(0.5f, 0.5f);
+    const pk2 zero = pk(0.f, 0.f);
     pa += (int64_t)rl * ld;
     if (DUAL) pb += (int64_t)rl * ld;
-    for (; i < nr; i += U * RL) {
-        Vec<VEC> x[U];
-        const bool full = (i + (U - 1) * RL) < nr;
-        if (full) {
+    const pk2 *cbp = cb2 + rl * K;
+    const int cstep = RL * K;
+    int left = (nr - rl + RL - 1) / RL;      // rows this thread owns
+    if (left < 0) left = 0;
+    // full blocks of U rows
+    for (; left >= U; left -= U) {
+        pk2 x0[U], x1[U];
 #pragma unroll
-            for (int u = 0; u < U; ++u) x[u] = load_row<VEC, DUAL>(pa + u * step, pb + u * step);
-        } else {
+        for (int u = 0; u < U; ++u) ldg_stream4(pa + u * step, x0[u], x1[u]);
+        if (DUAL) {
+            pk2 y0[U], y1[U];
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                if (i + u * RL < nr) x[u] = load_row<VEC, DUAL>(pa + u * step, pb + u * step);
-                else x[u] = zero_vec<VEC>();
+            for (int u = 0; u < U; ++u) ldg_stream4(pb + u * step, y0[u], y1[u]);
+#pragma unroll
+            for (int u = 0; u < U; ++u) {          // embedding.py:186: (prev + cur) / 2 in float32
+                x0[u] = mul2(add2(x0[u], y0[u]), half);
+                x1[u] = mul2(add2(x1[u], y1[u]), half);
             }
+            pb += U * step;
         }
-        float a32[K][VEC];
+        pk2 a0[K], a1[K];
 #pragma unroll
-        for (int k = 0; k < K; ++k)
-#pragma unroll
-            for (int v = 0; v < VEC; ++v) a32[k][v] = 0.f;
+        for (int k = 0; k < K; ++k) { a0[k] = zero; a1[k] = zero; }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const int row = i + u * RL;
-            const bool ok = full || row < nr;
-            float c[K];
+            const pk2 t0 = add2(x0[u], npiv0), t1 = add2(x1[u], npiv1);
 #pragma unroll
-            for (int k = 0; k < K; ++k) c[k] = ok ? cb[row * K + k] : 0.f;
-#pragma unroll
-            for (int v = 0; v < VEC; ++v) {
-                const float t = x[u].v[v] - piv[v];
-#pragma unroll
-                for (int k = 0; k < K; ++k) a32[k][v] = fmaf(t, c[k], a32[k][v]);
+            for (int k = 0; k < K; ++k) {
+                const pk2 c = cbp[u * cstep + k];
+                a0[k] = fma2(t0, c, a0[k]);
+                a1[k] = fma2(t1, c, a1[k]);
             }
         }
 #pragma unroll
-        for (int k = 0; k < K; ++k)
-#pragma unroll
-            for (int v = 0; v < VEC; ++v) acc[k][v] += (double)a32[k][v];
+        for (int k = 0; k < K; ++k) {
+            float f0, f1, f2, f3;
+            unpk(a0[k], f0, f1);
+            unpk(a1[k], f2, f3);
+            acc[k][0] += (double)f0; acc[k][1] += (double)f1;
+            acc[k][2] += (double)f2; acc[k][3] += (double)f3;
+        }
         pa += U * step;
-        if (DUAL) pb += U * step;
+        cbp += U * cstep;
     }
+    // tail (< U rows): predicated loads, same arithmetic
+    if (left > 0) {
+        pk2 x0[U], x1[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            x0[u] = zero; x1[u] = zero;
+            if (u < left) {
+                ldg_stream4(pa + u * step, x0[u], x1[u]);
+                if (DUAL) {
+                    pk2 y0, y1;
+                    ldg_stream4(pb + u * step, y0, y1);
+                    x0[u] = mul2(add2(x0[u], y0), half);
+                    x1[u] = mul2(add2(x1[u], y1), half);
+                }
+            }
+        }
+        pk2 a0[K], a1[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) { a0[k] = zero; a1[k] = zero; }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (u < left) {
+                const pk2 t0 = add2(x0[u], npiv0), t1 = add2(x1[u], npiv1);
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    const pk2 c = cbp[u * cstep + k];
+                    a0[k] = fma2(t0, c, a0[k]);
+                    a1[k] = fma2(t1, c, a1[k]);
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            float f0, f1, f2, f3;
+            unpk(a0[k], f0, f1);
+            unpk(a1[k], f2, f3);
+            acc[k][0] += (double)f0; acc[k][1] += (double)f1;
+            acc[k][2] += (double)f2; acc[k][3] += (double)f3;
+        }
+    }
+}
+
+// ---- pass 1, scalar path (D % 4 != 0 or rows not 16-byte aligned) ----
+template <int K, bool DUAL>
+__device__ __forceinline__ void stream_piece1(const float *pa, const float *pb, int64_t ld, int nr, int rl,
+                                              int RL, const pk2 *cb2, float piv, double (&acc)[K][4]) {
+    constexpr int U = 8;
+    for (int i0 = rl; i0 < nr; i0 += U * RL) {
+        float x[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int i = i0 + u * RL;
+            x[u] = 0.f;
+            if (i < nr) {
+                x[u] = ldg_stream1(pa + (int64_t)i * ld);
+                if (DUAL) x[u] = (x[u] + ldg_stream1(pb + (int64_t)i * ld)) * 0.5f;
+            }
+        }
+        float a32[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) a32[k] = 0.f;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int i = i0 + u * RL;
+            if (i < nr) {
+                const float t = x[u] - piv;
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    float c, c_;
+                    unpk(cb2[i * K + k], c, c_);
+                    a32[k] = fmaf(t, c, a32[k]);
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < K; ++k) acc[k][0] += (double)a32[k];
+    }
+}
+
+// extended cosine table for pass 2a: T[i] = cos(pi * (i mod 4D) / 2D), i < 4D + 8m
+__global__ void fp_table_kernel(float *T, int D, int len) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < len; i += gridDim.x * blockDim.x)
+        T[i] = (float)cospi((double)(i % (4 * D)) / (2.0 * D));
 }
 
 // ------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------
-// MAXT/MINB: launch bounds.  CTAs of <= 320 threads are compiled for 3 CTAs per SM (<= 64
-// registers) so that ~3 x 320 threads x U x 16 B of loads are in flight per SM.
+// MAXT/MINB: launch bounds (registers per thread are capped at 65536 / (MAXT * MINB)).
 template <int K, int VEC, int U, int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB) fp_kernel(const Params p) {
     constexpr int N = K + 1;
     extern __shared__ __align__(16) unsigned char smem[];
-    float *T4D = reinterpret_cast<float *>(smem + p.lay.off_t4d);    // cos(pi i / 2D), i < 4D
-    float *Y = reinterpret_cast<float *>(smem + p.lay.off_y);        // [N][D] pass-1 result - 0.5
-    float *cb = reinterpret_cast<float *>(smem + p.lay.off_cb);      // [rows][K] basis of the item
+    float *TT = reinterpret_cast<float *>(smem + p.lay.off_t4d);     // cos table (extended), pass 2a
+    float *Y = reinterpret_cast<float *>(smem + p.lay.off_y);        // [N][D] pass-1 result, folded
+    pk2 *cb2 = reinterpret_cast<pk2 *>(smem + p.lay.off_cb);         // [rows][K] (c, c) basis of the item
     double *scr = reinterpret_cast<double *>(smem + p.lay.off_scr);  // u sums, later F / Z
     double *Tm = reinterpret_cast<double *>(smem + p.lay.off_tm);    // cos(pi i / 2m), i < 4m
     double *Mj = reinterpret_cast<double *>(smem + p.lay.off_mj);    // [N][K] cos(pi (2j+1) k / 2n)
     __shared__ int s_item, s_flag, s_last;
+    __shared__ double s_mn[kMaxN], s_mx[kMaxN];
+    __shared__ int s_bad[kMaxN];
 
-    const int tid = threadIdx.x, T = blockDim.x;
+    const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5;
     const int D = p.D, m = p.m;
     const int G = p.lay.G, RL = p.lay.RL, CT = p.lay.CT;
+    const int nk = m - 1;
+    const int DS = max(1, T / nk);
+    const int half = D / 2;
 
-    // ---- per-CTA tables (the CTA is persistent: built once) ----
-    for (int i = tid; i < 4 * D; i += T) T4D[i] = (float)cospi((double)i / (2.0 * D));
+    // ---- per-CTA tables (the CTA is persistent: loaded / built once) ----
+    for (int i = tid; i < p.lay.table_len; i += T) TT[i] = __ldg(p.table + i);
     for (int i = tid; i < 4 * m; i += T) Tm[i] = cospi((double)i / (2.0 * m));
     for (int i = tid; i < N * K; i += T) {
         const int j = i / K, k = i % K + 1;
@@ -245,11 +332,19 @@ __global__ void __launch_bounds__(MAXT, MINB) fp_kernel(const Params p) {
         const DomInfo dom = p.doms[item.dom];
         const int L = dom.L, r0 = item.r0, r1 = item.r1;
 
-        // ---- basis for this item's rows: cos(pi (2l+1) k / 2L), argument reduced exactly ----
-        for (int i = tid; i < (r1 - r0) * K; i += T) {
-            const int l = r0 + i / K, k = i % K + 1;
-            const long long q = ((long long)(2 * l + 1) * k) % (4LL * L);
-            cb[i] = (float)cospi((double)q / (2.0 * L));
+        // ---- basis of this item's rows: c_k = cos(pi (2l+1) k / 2L) by the Chebyshev recurrence
+        //      c_k = 2 c_1 c_{k-1} - c_{k-2} in float64 from one cospi per row ----
+        for (int r = tid; r < r1 - r0; r += T) {
+            const double c1 = cospi((double)(2 * (r0 + r) + 1) / (2.0 * L));
+            double ckm2 = 1.0, ckm1 = c1;
+            cb2[r * K] = pk((float)c1, (float)c1);
+#pragma unroll
+            for (int k = 2; k <= K; ++k) {
+                const double ck = 2.0 * c1 * ckm1 - ckm2;
+                cb2[r * K + k - 1] = pk((float)ck, (float)ck);
+                ckm2 = ckm1;
+                ckm1 = ck;
+            }
         }
         __syncthreads();
 
@@ -259,37 +354,57 @@ __global__ void __launch_bounds__(MAXT, MINB) fp_kernel(const Params p) {
             const int g = g0 + ct * T;
             const bool active = lane_ok && g < G;
             const int col = g * VEC;
-            double acc[K][VEC];
+            double acc[K][4];
 #pragma unroll
             for (int k = 0; k < K; ++k)
 #pragma unroll
-                for (int v = 0; v < VEC; ++v) acc[k][v] = 0.0;
+                for (int v = 0; v < 4; ++v) acc[k][v] = 0.0;
             if (active) {
                 // pivot = row 0 of the domain (same for every split of the domain)
-                float piv[VEC];
-                {
-                    const float *pa = src[first.src_a] + (int64_t)first.row_a * p.ld + col;
-                    Vec<VEC> a = Vec<VEC>::load(pa);
-                    if (first.src_b >= 0) {
-                        Vec<VEC> b = Vec<VEC>::load(src[first.src_b] + (int64_t)first.row_b * p.ld + col);
-#pragma unroll
-                        for (int v = 0; v < VEC; ++v) a.v[v] = (a.v[v] + b.v[v]) * 0.5f;
+                const float *fa = src[first.src_a] + (int64_t)first.row_a * p.ld + col;
+                const float *fb = (first.src_b >= 0) ? src[first.src_b] + (int64_t)first.row_b * p.ld + col : nullptr;
+                if constexpr (VEC == 4) {
+                    pk2 v0, v1;
+                    ldg_stream4(fa, v0, v1);
+                    if (fb) {
+                        pk2 w0, w1;
+                        ldg_stream4(fb, w0, w1);
+                        const pk2 hf = pk(0.5f, 0.5f);
+                        v0 = mul2(add2(v0, w0), hf);
+                        v1 = mul2(add2(v1, w1), hf);
                     }
-#pragma unroll
-                    for (int v = 0; v < VEC; ++v) piv[v] = a.v[v];
-                }
-                for (int pi = item.piece_first; pi < dom.n_pieces; ++pi) {
-                    const Piece pc = p.pieces[dom.piece_off + pi];
-                    if (pc.l0 >= r1) break;
-                    const int a = max(pc.l0, r0), b = min(pc.l0 + pc.nrows, r1);
-                    if (a >= b) continue;
-                    const float *pa = src[pc.src_a] + (int64_t)(pc.row_a + (a - pc.l0)) * p.ld + col;
-                    const float *cbp = cb + (a - r0) * K;
-                    if (pc.src_b < 0) {
-                        stream_piece<K, VEC, U, false>(pa, pa, p.ld, b - a, rl, RL, cbp, piv, acc);
-                    } else {
-                        const float *pb = src[pc.src_b] + (int64_t)(pc.row_b + (a - pc.l0)) * p.ld + col;
-                        stream_piece<K, VEC, U, true>(pa, pb, p.ld, b - a, rl, RL, cbp, piv, acc);
+                    const pk2 neg = pk(-1.f, -1.f);
+                    const pk2 npiv0 = mul2(v0, neg), npiv1 = mul2(v1, neg);
+                    for (int pi = item.piece_first; pi < dom.n_pieces; ++pi) {
+                        const Piece pc = p.pieces[dom.piece_off + pi];
+                        if (pc.l0 >= r1) break;
+                        const int a = max(pc.l0, r0), b = min(pc.l0 + pc.nrows, r1);
+                        if (a >= b) continue;
+                        const float *pa = src[pc.src_a] + (int64_t)(pc.row_a + (a - pc.l0)) * p.ld + col;
+                        const pk2 *cbp = cb2 + (a - r0) * K;
+                        if (pc.src_b < 0) {
+                            stream_piece4<K, U, false>(pa, pa, p.ld, b - a, rl, RL, cbp, npiv0, npiv1, acc);
+                        } else {
+                            const float *pb = src[pc.src_b] + (int64_t)(pc.row_b + (a - pc.l0)) * p.ld + col;
+                            stream_piece4<K, U, true>(pa, pb, p.ld, b - a, rl, RL, cbp, npiv0, npiv1, acc);
+                        }
+                    }
+                } else {
+                    float piv = ldg_stream1(fa);
+                    if (fb) piv = (piv + ldg_stream1(fb)) * 0.5f;
+                    for (int pi = item.piece_first; pi < dom.n_pieces; ++pi) {
+                        const Piece pc = p.pieces[dom.piece_off + pi];
+                        if (pc.l0 >= r1) break;
+                        const int a = max(pc.l0, r0), b = min(pc.l0 + pc.nrows, r1);
+                        if (a >= b) continue;
+                        const float *pa = src[pc.src_a] + (int64_t)(pc.row_a + (a - pc.l0)) * p.ld + col;
+                        const pk2 *cbp = cb2 + (a - r0) * K;
+                        if (pc.src_b < 0) {
+                            stream_piece1<K, false>(pa, pa, p.ld, b - a, rl, RL, cbp, piv, acc);
+                        } else {
+                            const float *pb = src[pc.src_b] + (int64_t)(pc.row_b + (a - pc.l0)) * p.ld + col;
+                            stream_piece1<K, true>(pa, pb, p.ld, b - a, rl, RL, cbp, piv, acc);
+                        }
                     }
                 }
             }
@@ -342,59 +457,107 @@ __global__ void __launch_bounds__(MAXT, MINB) fp_kernel(const Params p) {
             __syncthreads();
         }
 
-        // ---- length-n inverse + per-column min-max (fingerprint.py:138-140 on [D, n]) ----
+        // ---- length-n inverse + per-column min-max (fingerprint.py:138-140 on [D, n]); Y = y' - 0.5 ----
         for (int d = tid; d < D; d += T) {
             double u[K], y[N];
 #pragma unroll
             for (int k = 0; k < K; ++k) u[k] = scr[k * D + d];
             double mn = INFINITY, mx = -INFINITY;
+            bool bad = false;
 #pragma unroll
             for (int j = 0; j < N; ++j) {
                 double s = 0.0;
 #pragma unroll
                 for (int k = 0; k < K; ++k) s = fma(Mj[j * K + k], u[k], s);
                 y[j] = s;
+                bad = bad || !(s == s);
                 mn = fmin(mn, s);
                 mx = fmax(mx, s);
             }
-            bool bad = !(mx > mn);
-#pragma unroll
-            for (int j = 0; j < N; ++j) bad = bad || isnan(y[j]);
+            bad = bad || !(mx > mn);
             if (bad) s_flag = 1;   // constant / non-finite column: the reference yields NaN -> all 0
+            const double inv = 1.0 / (mx - mn);
 #pragma unroll
-            for (int j = 0; j < N; ++j) Y[j * D + d] = (float)((y[j] - mn) / (mx - mn) - 0.5);
+            for (int j = 0; j < N; ++j) Y[j * D + d] = (float)((y[j] - mn) * inv - 0.5);
+        }
+        __syncthreads();
+        // fold: cos(pi (2(D-1-d)+1) k / 2D) = (-1)^k cos(pi (2d+1) k / 2D), so even k only need
+        // e[d] = Y[d] + Y[D-1-d] (kept at index d) and odd k only o[d] = Y[d] - Y[D-1-d] (at D-1-d)
+        for (int i = tid; i < N * half; i += T) {
+            const int j = i / half, d = i % half;
+            const float a = Y[j * D + d], b = Y[j * D + D - 1 - d];
+            Y[j * D + d] = a + b;
+            Y[j * D + D - 1 - d] = a - b;
         }
         __syncthreads();
 
-        // ---- pass 2a: F[j][k] = sum_d Y[j][d] cos(pi (2d+1) k / 2D), k = 1..m-1 ----
-        const int nk = m - 1;
-        const int DS = max(1, T / nk);
-        double *Fp = scr;                       // [DS][N][nk]
-        double *Z = scr + (size_t)DS * N * nk;  // [N][m]
+        // ---- pass 2a: F[j][k] = sum_{d < D/2} (e|o)[j][d] cos(pi (2d+1) k / 2D) (+ middle column) ----
+        double *Fp = scr;                                  // [DS][N][nk]
+        double *Fr = scr + (size_t)DS * N * nk;            // [N][nk]
+        double *Z = Fr + (size_t)N * nk;                   // [N][m]
         for (int w = tid; w < nk * DS; w += T) {
             const int k = 1 + w % nk, ds = w / nk;
-            const int d0 = (int)((int64_t)D * ds / DS), d1 = (int)((int64_t)D * (ds + 1) / DS);
+            const bool odd = (k & 1) != 0;
+            // split boundaries are multiples of 4 so that 16-byte shared loads stay aligned
+            int d0 = (int)((int64_t)(half / 4) * ds / DS) * 4;
+            int d1 = (ds == DS - 1) ? half : (int)((int64_t)(half / 4) * (ds + 1) / DS) * 4;
             int idx = (int)(((long long)(2 * d0 + 1) * k) % (4LL * D));
-            const int stepk = 2 * k;
+            const int s1 = 2 * k, s2 = 4 * k, s3 = 6 * k, s4 = 8 * k;
             double f64[N];
             float f32[N];
 #pragma unroll
             for (int j = 0; j < N; ++j) { f64[j] = 0.0; f32[j] = 0.f; }
-            int run = 0;
-            for (int d = d0; d < d1; ++d) {
-                const float c = T4D[idx];
-                idx += stepk;
+            int d = d0;
+            if constexpr (VEC == 4) {
+                int run = 0;
+                for (; d + 3 < d1; d += 4) {
+                    const float c0 = TT[idx], c1 = TT[idx + s1], c2 = TT[idx + s2], c3 = TT[idx + s3];
+                    idx += s4;
+                    while (idx >= 4 * D) idx -= 4 * D;
+#pragma unroll
+                    for (int j = 0; j < N; ++j) {
+                        float4 v;
+                        if (!odd) {
+                            v = *reinterpret_cast<const float4 *>(Y + j * D + d);
+                        } else {
+                            const float4 t = *reinterpret_cast<const float4 *>(Y + j * D + D - 4 - d);
+                            v = make_float4(t.w, t.z, t.y, t.x);
+                        }
+                        f32[j] = fmaf(v.x, c0, f32[j]);
+                        f32[j] = fmaf(v.y, c1, f32[j]);
+                        f32[j] = fmaf(v.z, c2, f32[j]);
+                        f32[j] = fmaf(v.w, c3, f32[j]);
+                    }
+                    if (++run == 8) {       // float32 chains of 32 terms, then float64
+#pragma unroll
+                        for (int j = 0; j < N; ++j) { f64[j] += (double)f32[j]; f32[j] = 0.f; }
+                        run = 0;
+                    }
+                }
+            }
+            for (; d < d1; ++d) {           // scalar path / leftovers
+                const float c = TT[idx];
+                idx += s1;
                 if (idx >= 4 * D) idx -= 4 * D;
 #pragma unroll
-                for (int j = 0; j < N; ++j) f32[j] = fmaf(Y[j * D + d], c, f32[j]);
-                if (++run == 32) {
-#pragma unroll
-                    for (int j = 0; j < N; ++j) { f64[j] += (double)f32[j]; f32[j] = 0.f; }
-                    run = 0;
+                for (int j = 0; j < N; ++j) {
+                    const float v = odd ? Y[j * D + D - 1 - d] : Y[j * D + d];
+                    f64[j] += (double)(v * c);
                 }
+            }
+            if ((D & 1) && ds == 0 && !odd) {   // middle column of an odd D pairs with itself
+                const float c = TT[(int)(((long long)D * k) % (4LL * D))];
+#pragma unroll
+                for (int j = 0; j < N; ++j) f64[j] += (double)(Y[j * D + half] * c);
             }
 #pragma unroll
             for (int j = 0; j < N; ++j) Fp[((size_t)ds * N + j) * nk + (k - 1)] = f64[j] + (double)f32[j];
+        }
+        __syncthreads();
+        for (int i = tid; i < N * nk; i += T) {
+            double f = 0.0;
+            for (int ds = 0; ds < DS; ++ds) f += Fp[(size_t)ds * N * nk + i];
+            Fr[i] = f;
         }
         __syncthreads();
 
@@ -403,34 +566,42 @@ __global__ void __launch_bounds__(MAXT, MINB) fp_kernel(const Params p) {
             const int j = w / m, c = w % m;
             int idx = 0;
             const int stepc = 2 * c + 1;
+            const double *fr = Fr + j * nk;
             double z = 0.0;
-            for (int k = 1; k <= nk; ++k) {
+            for (int k = 0; k < nk; ++k) {
                 idx += stepc;
                 if (idx >= 4 * m) idx -= 4 * m;
-                double f = 0.0;
-                for (int ds = 0; ds < DS; ++ds) f += Fp[((size_t)ds * N + j) * nk + (k - 1)];
-                z = fma(Tm[idx], f, z);
+                z = fma(Tm[idx], fr[k], z);
             }
             Z[w] = z;
         }
         __syncthreads();
 
-        // ---- per-row min-max, *127, truncating int8 cast (fingerprint.py:193-195) ----
+        // ---- per-row min-max (one warp per row), *127, truncating int8 cast (fingerprint.py:193-195) ----
+        for (int j = warp; j < N; j += (T >> 5)) {
+            double mn = INFINITY, mx = -INFINITY;
+            int bad = 0;
+            for (int c = lane; c < m; c += 32) {
+                const double z = Z[j * m + c];
+                bad |= !(z == z);
+                mn = fmin(mn, z);
+                mx = fmax(mx, z);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+                mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+                bad |= __shfl_xor_sync(0xffffffffu, bad, o);
+            }
+            if (lane == 0) { s_mn[j] = mn; s_mx[j] = mx; s_bad[j] = bad || !(mx > mn); }
+        }
+        __syncthreads();
         const bool layer_bad = s_flag != 0;
         int8_t *out = p.out + (int64_t)item.dom * p.out_stride + (int64_t)item.layer * (N * m);
         for (int w = tid; w < N * m; w += T) {
             const int j = w / m;
-            double mn = INFINITY, mx = -INFINITY;
-            bool bad = layer_bad;
-            for (int c = 0; c < m; ++c) {
-                const double z = Z[j * m + c];
-                bad = bad || isnan(z);
-                mn = fmin(mn, z);
-                mx = fmax(mx, z);
-            }
-            bad = bad || !(mx > mn);
             int q = 0;
-            if (!bad) q = (int)(((Z[w] - mn) / (mx - mn)) * 127.0);
+            if (!layer_bad && !s_bad[j]) q = (int)(((Z[w] - s_mn[j]) / (s_mx[j] - s_mn[j])) * 127.0);
             out[w] = (int8_t)q;
         }
     }
@@ -456,11 +627,12 @@ Layout make_layout(int D, int n, int m, bool vec4) {
     l.T = std::max(l.T, 128);
     const int nk = m - 1;
     const int DS = std::max(1, l.T / nk);
+    l.table_len = 4 * D + 8 * m;
     size_t off = 0;
-    l.off_t4d = off; off += dctd::align_up((size_t)4 * D * sizeof(float), 16);
+    l.off_t4d = off; off += dctd::align_up((size_t)l.table_len * sizeof(float), 16);
     l.off_y = off;   off += dctd::align_up((size_t)n * D * sizeof(float), 16);
-    l.off_cb = off;  off += dctd::align_up((size_t)kRowsPerItem * K * sizeof(float), 16);
-    const size_t scr = std::max((size_t)K * D, (size_t)DS * n * nk + (size_t)n * m) * sizeof(double);
+    l.off_cb = off;  off += dctd::align_up((size_t)kRowsPerItem * K * sizeof(unsigned long long), 16);
+    const size_t scr = std::max((size_t)K * D, (size_t)DS * n * nk + (size_t)n * nk + (size_t)n * m) * sizeof(double);
     l.off_scr = off; off += dctd::align_up(scr, 16);
     l.off_tm = off;  off += dctd::align_up((size_t)4 * m * sizeof(double), 16);
     l.off_mj = off;  off += dctd::align_up((size_t)n * K * sizeof(double), 16);
@@ -603,6 +775,7 @@ int dctd_fp_plan_create(const dctd_fp_geometry *geo, dctd_fp_plan **out_plan) {
             pl->blob_bytes = off;
             pl->off_src = off;      off += dctd::align_up((size_t)geo->n_layers * geo->n_src * sizeof(void *), 256);
             pl->off_counters = off; off += dctd::align_up((size_t)n_counters * sizeof(int), 256);
+            pl->off_table = off;    off += dctd::align_up((size_t)(4 * geo->D + 8 * geo->m) * sizeof(float), 256);
             pl->off_partials = off; off += dctd::align_up((size_t)n_slabs * (geo->n - 1) * geo->D * sizeof(double), 256);
             pl->total = off;
             if (pl->blob_bytes) {
@@ -687,12 +860,16 @@ int dctd_fp_execute(const dctd_fp_plan *plan, const void *const *h_src_ptrs, int
     DCTD_CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
     if (prm.lay.smem > (size_t)max_smem) return DCTD_ERR_UNSUPPORTED;
 
-    if (!(flags & DCTD_FP_TABLES_RESIDENT))
+    if (!(flags & DCTD_FP_TABLES_RESIDENT)) {
         DCTD_CUDA_TRY(cudaMemcpyAsync(ws, plan->blob, plan->blob_bytes, cudaMemcpyHostToDevice, stream));
+        fp_table_kernel<<<8, 256, 0, stream>>>((float *)(ws + plan->off_table), plan->D, prm.lay.table_len);
+        DCTD_LAUNCH_CHECK();
+    }
     DCTD_CUDA_TRY(cudaMemcpyAsync(ws + plan->off_src, h_src_ptrs, nptr * sizeof(void *), cudaMemcpyHostToDevice, stream));
     DCTD_CUDA_TRY(cudaMemsetAsync(ws + plan->off_counters, 0, (size_t)plan->n_counters * sizeof(int), stream));
 
     prm.src = (const float *const *)(ws + plan->off_src);
+    prm.table = (const float *)(ws + plan->off_table);
     prm.pieces = (const Piece *)(ws + plan->off_pieces);
     prm.doms = (const DomInfo *)(ws + plan->off_doms);
     prm.items = (const Item *)(ws + plan->off_items);
