@@ -7,7 +7,7 @@
 Primary line = BASELINE.json metric part (i), domain fingerprints/s, on configs[1]:
   100k synthetic domains, L ~ U{40..500}, two ESM-2 layers x 1280 fp32.  A step is one batch of
   --batch domains (default 4096, ~11 GB of embeddings: far larger than the 126 MB L2); the
-  default 25 steps cover 102,400 domains.  `value` times the kernel path with inputs resident in
+  default 200 steps stream 819,200 domains (8x the 100k of configs[1], ~0.4 s timed).  `value` times the kernel path with inputs resident in
   HBM; `e2e` times the public Python API (`quantize_batch` on Fingerprint objects) with pinned host
   embeddings, H2D + kernel + D2H inside the timed region.
 The same JSON line carries `search`: part (ii) of the metric, L1 top-50 query.DB pairs/s on a
@@ -76,7 +76,9 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    per_step = max(cores * 16, 64)
+    r0, _ = cpu_fingerprint_rate(max(cores * 2, 16), cores)           # calibration, untimed
+    budget_s = 60.0 / max(1, args.steps + args.warmup)                # whole run ~1 minute
+    per_step = int(min(max(r0 * min(budget_s, 3.0), cores * 2), 5000))
     rates = []
     for s in range(args.warmup + args.steps):
         r, dt = cpu_fingerprint_rate(per_step, cores)
@@ -116,7 +118,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
-                                          '-lms', '100', '-i', str(self.index)], stdout=subprocess.PIPE,
+                                          '-lms', '20', '-i', str(self.index)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
         except OSError:
             self.proc = None
@@ -219,12 +221,18 @@ def run_ours(args):
         plan, layers, out, ws = pool[i % len(pool)]
         execute_plan(plan, [[layers[0]], [layers[1]]], out, tables_resident=True, workspace=ws)
 
-    for i in range(args.warmup):
-        step(i)
-    barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    # warm-up: at least W steps and at least ~0.3 s, so that clocks are at their loaded level
+    t_w = time.perf_counter()
+    i = 0
+    while i < args.warmup or time.perf_counter() - t_w < 0.3:
+        step(i)
+        i += 1
+        if i % 8 == 0:
+            torch.cuda.synchronize()
+    barrier()
     L.dctd_launch_count(1)
     evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     barrier()
@@ -286,7 +294,8 @@ def run_ours(args):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cores = os.cpu_count() or 1
-        n = max(cores * 6, 48)
+        r0, _ = cpu_fingerprint_rate(max(cores * 2, 16), cores)       # calibration
+        n = int(min(max(r0 * 12.0, cores * 4), 20000))                # ~12 s of CPU work
         r, dt = cpu_fingerprint_rate(n, cores)
         cpu = {'value': r, 'unit': 'fingerprints/s', 'cores': cores, 'kind': 'port', 'seconds': dt,
                'sample': f'{n} domains, L~U{{{LMIN}..{LMAX}}}, {LAYERS}x{D} fp32: oracle port of reference '
@@ -364,7 +373,7 @@ def run_search(args, dev, rank, world, dist, torch, dindex, ShardedIndex, shard_
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=25)
+    ap.add_argument('--steps', type=int, default=200)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--batch', type=int, default=4096, help='domains per step')
