@@ -142,12 +142,32 @@ __device__ __forceinline__ float ldg_stream1(const float *p) {
     return r;
 }
 
+// the K (c, c) pairs of one row; 16-byte shared loads when K is even
+template <int K>
+__device__ __forceinline__ void load_basis(const pk2 *p, pk2 (&c)[K]) {
+    if constexpr (K % 2 == 0) {
+#pragma unroll
+        for (int k = 0; k < K; k += 2) {
+            const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(p + k);
+            c[k] = v.x;
+            c[k + 1] = v.y;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < K; ++k) c[k] = p[k];
+    }
+}
+
 // ---- pass 1, float4 path: rows rl, rl+RL, ... of one piece; acc[k] += (x - pivot) * c_k[row] ----
 // cb2[row*K + k] holds (c, c) so that one FFMA2 covers two columns.
-template <int K, int U, bool DUAL>
-__device__ __forceinline__ void stream_piece4(const float *pa, const float *pb, int64_t ld, int nr, int rl,
-                                              int RL, const pk2 *cb2, pk2 npiv0, pk2 npiv1,
+// LDC / RLC: compile-time row stride (floats) and row-lane count for the common ESM-2 widths (0 = runtime);
+// with them every load of a block is base + immediate and the address arithmetic disappears.
+template <int K, int U, bool DUAL, int LDC, int RLC>
+__device__ __forceinline__ void stream_piece4(const float *pa, const float *pb, int64_t ld_, int nr, int rl,
+                                              int RL_, const pk2 *cb2, pk2 npiv0, pk2 npiv1,
                                               double (&acc)[K][4]) {
+    const int RL = RLC ? RLC : RL_;
+    const int64_t ld = LDC ? (int64_t)LDC : ld_;
     const int64_t step = (int64_t)RL * ld;
     const pk2 half = pk(0.5f, 0.5f);
     const pk2 zero = pk(0.f, 0.f);
@@ -179,11 +199,12 @@ __device__ __forceinline__ void stream_piece4(const float *pa, const float *pb, 
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const pk2 t0 = add2(x0[u], npiv0), t1 = add2(x1[u], npiv1);
+            pk2 c[K];
+            load_basis<K>(cbp + u * cstep, c);
 #pragma unroll
             for (int k = 0; k < K; ++k) {
-                const pk2 c = cbp[u * cstep + k];
-                a0[k] = fma2(t0, c, a0[k]);
-                a1[k] = fma2(t1, c, a1[k]);
+                a0[k] = fma2(t0, c[k], a0[k]);
+                a1[k] = fma2(t1, c[k], a1[k]);
             }
         }
 #pragma unroll
@@ -220,11 +241,12 @@ __device__ __forceinline__ void stream_piece4(const float *pa, const float *pb, 
         for (int u = 0; u < U; ++u) {
             if (u < left) {
                 const pk2 t0 = add2(x0[u], npiv0), t1 = add2(x1[u], npiv1);
+                pk2 c[K];
+                load_basis<K>(cbp + u * cstep, c);
 #pragma unroll
                 for (int k = 0; k < K; ++k) {
-                    const pk2 c = cbp[u * cstep + k];
-                    a0[k] = fma2(t0, c, a0[k]);
-                    a1[k] = fma2(t1, c, a1[k]);
+                    a0[k] = fma2(t0, c[k], a0[k]);
+                    a1[k] = fma2(t1, c[k], a1[k]);
                 }
             }
         }
@@ -286,7 +308,7 @@ __global__ void fp_table_kernel(float *T, int D, int len) {
 // the kernel
 // ------------------------------------------------------------------------------------------
 // MAXT/MINB: launch bounds (registers per thread are capped at 65536 / (MAXT * MINB)).
-template <int K, int VEC, int U, int MAXT, int MINB>
+template <int K, int VEC, int U, int MAXT, int MINB, int LDC = 0, int RLC = 0>
 __global__ void __launch_bounds__(MAXT, MINB) fp_kernel(const Params p) {
     constexpr int N = K + 1;
     extern __shared__ __align__(16) unsigned char smem[];
@@ -383,10 +405,10 @@ __global__ void __launch_bounds__(MAXT, MINB) fp_kernel(const Params p) {
                         const float *pa = src[pc.src_a] + (int64_t)(pc.row_a + (a - pc.l0)) * p.ld + col;
                         const pk2 *cbp = cb2 + (a - r0) * K;
                         if (pc.src_b < 0) {
-                            stream_piece4<K, U, false>(pa, pa, p.ld, b - a, rl, RL, cbp, npiv0, npiv1, acc);
+                            stream_piece4<K, U, false, LDC, RLC>(pa, pa, p.ld, b - a, rl, RL, cbp, npiv0, npiv1, acc);
                         } else {
                             const float *pb = src[pc.src_b] + (int64_t)(pc.row_b + (a - pc.l0)) * p.ld + col;
-                            stream_piece4<K, U, true>(pa, pb, p.ld, b - a, rl, RL, cbp, npiv0, npiv1, acc);
+                            stream_piece4<K, U, true, LDC, RLC>(pa, pb, p.ld, b - a, rl, RL, cbp, npiv0, npiv1, acc);
                         }
                     }
                 } else {
@@ -890,8 +912,12 @@ int dctd_fp_execute(const dctd_fp_plan *plan, const void *const *h_src_ptrs, int
         // tuning variants of the common case n = 3 (see DESIGN.md "pass-1 occupancy")
         if (K == 2 && g_variant == 1) fn = fp_kernel<2, 4, 4, 320, 3>;
         else if (K == 2 && g_variant == 2) fn = fp_kernel<2, 4, 8, 320, 3>;
+        else if (K == 2 && ld == plan->D && plan->D == 1280 && prm.lay.RL == 1) fn = fp_kernel<2, 4, 8, 320, 2, 1280, 1>;
+        else if (K == 2 && ld == plan->D && plan->D == 640 && prm.lay.RL == 2) fn = fp_kernel<2, 4, 8, 320, 2, 640, 2>;
+        else if (K == 2 && ld == plan->D && plan->D == 320 && prm.lay.RL == 4) fn = fp_kernel<2, 4, 8, 320, 2, 320, 4>;
         else fn = pick_k<4, 8, 320, 2>(K);
-    } else fn = pick_k<4, 8, kMaxThreads, 1>(K);
+    } else if (K == 2 && ld == plan->D && plan->D == 2560 && prm.lay.RL == 1) fn = fp_kernel<2, 4, 8, kMaxThreads, 1, 2560, 1>;
+    else fn = pick_k<4, 8, kMaxThreads, 1>(K);
     if (!fn) return DCTD_ERR_UNSUPPORTED;
     DCTD_CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prm.lay.smem));
     int per_sm = 0;

@@ -31,8 +31,8 @@
 namespace {
 
 constexpr int kWarps = 8;            // warps per CTA of the scan kernel
-constexpr int kTDmax = 4;            // database groups (of 32 vectors) per shared-memory stage (1 for wide d)
-constexpr int kStages = 2;
+constexpr int kTDmax = 2;            // database groups (of 32 vectors) per shared-memory stage (1 for wide d)
+constexpr int kStagesMax = 4;        // TMA stages (2 for wide d)
 constexpr int kIdBits = 40;          // key = dist << 40 | position
 constexpr unsigned long long kKeyMax = ~0ULL;
 constexpr unsigned long long kIdMask = (1ULL << kIdBits) - 1ULL;
@@ -143,6 +143,24 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned int 
             : "memory");
     }
 }
+// producer-side wait: sleeps between probes so that the spinning lane does not take issue slots from
+// the compute warps of its scheduler
+__device__ __forceinline__ void mbar_wait_backoff(unsigned long long *bar, unsigned int parity) {
+    unsigned int done = 0;
+    for (;;) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (done) break;
+        __nanosleep(400);
+    }
+}
 __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned int bytes, unsigned long long *bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                      smem_u32(dst)),
@@ -169,17 +187,25 @@ struct ScanParams {
     long long n_groups, groups_per_split;
 };
 
-template <int TQ, int kTD>
-__global__ void __launch_bounds__(kWarps * 32, 1) l1_scan_kernel(const ScanParams p) {
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// Warp-specialised scan: warp kWarps is the TMA producer (one elected lane), warps 0..kWarps-1 compute.
+// Stages are handed over with full/empty mbarriers, so compute warps never meet at a CTA barrier and
+// drift apart: while one warp filters candidates, the others keep the integer pipe busy.
+template <int TQ, int kTD, int STAGES>
+__global__ void __launch_bounds__((kWarps + 1) * 32, 1) l1_scan_kernel(const ScanParams p) {
     constexpr int QT = kWarps * TQ;
     extern __shared__ __align__(128) unsigned char smem[];
     const int C = chunks_of(p.d);
     const int dpad = C * 16;
     const int tile_bytes = kTD * 32 * dpad;
-    unsigned long long *bars = reinterpret_cast<unsigned long long *>(smem);           // [kStages]
+    unsigned long long *full = reinterpret_cast<unsigned long long *>(smem);           // [STAGES]
+    unsigned long long *empty = full + STAGES;                                          // [STAGES]
     unsigned char *qs = smem + 128;                                                     // [QT][dpad]
-    unsigned char *st = qs + (size_t)QT * dpad;                                         // [kStages][tile]
-    unsigned long long *buf = reinterpret_cast<unsigned long long *>(st + (size_t)kStages * tile_bytes);
+    unsigned char *st = qs + (size_t)QT * dpad;                                         // [STAGES][tile]
+    unsigned long long *buf = reinterpret_cast<unsigned long long *>(st + (size_t)STAGES * tile_bytes);
     unsigned long long *thr = buf + (size_t)QT * p.cap;                                 // [QT]
     int *cnt = reinterpret_cast<int *>(thr + QT);                                       // [QT]
 
@@ -190,7 +216,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) l1_scan_kernel(const ScanParam
     const int n_tiles = (int)((g_end - g_begin + kTD - 1) / kTD);
 
     if (tid == 0) {
-        for (int s = 0; s < kStages; ++s) mbar_init(&bars[s], 1);
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     // queries -> shared memory, biased by 0x80, zero-distance padding beyond d / nq
@@ -203,25 +229,35 @@ __global__ void __launch_bounds__(kWarps * 32, 1) l1_scan_kernel(const ScanParam
     for (int i = tid; i < QT; i += blockDim.x) { thr[i] = kKeyMax; cnt[i] = 0; }
     __syncthreads();
 
-    auto issue = [&](int t) {   // thread 0: TMA bulk copy of tile t into its stage
-        const long long g = g_begin + (long long)t * kTD;
-        const int ng = (int)min((long long)kTD, g_end - g);
-        const unsigned int bytes = (unsigned int)ng * 32u * (unsigned int)dpad;
-        unsigned long long *bar = &bars[t % kStages];
-        mbar_expect_tx(bar, bytes);
-        bulk_g2s(st + (size_t)(t % kStages) * tile_bytes, p.packed + g * C * 32, bytes, bar);
-    };
-    if (tid == 0)
-        for (int t = 0; t < min(kStages, n_tiles); ++t) issue(t);
+    if (warp == kWarps) {
+        // ---------------- producer ----------------
+        if (lane == 0) {
+            for (int t = 0; t < n_tiles; ++t) {
+                const int s = t % STAGES;
+                if (t >= STAGES) mbar_wait_backoff(&empty[s], (unsigned int)(((t / STAGES) - 1) & 1));
+                const long long g = g_begin + (long long)t * kTD;
+                const int ng = (int)min((long long)kTD, g_end - g);
+                const unsigned int bytes = (unsigned int)ng * 32u * (unsigned int)dpad;
+                mbar_expect_tx(&full[s], bytes);
+                bulk_g2s(st + (size_t)s * tile_bytes, p.packed + g * C * 32, bytes, &full[s]);
+            }
+        }
+        return;
+    }
 
+    // ---------------- consumers ----------------
     const uint4 *qs4 = reinterpret_cast<const uint4 *>(qs) + (size_t)warp * TQ * C;
     unsigned long long *wbuf = buf + (size_t)warp * TQ * p.cap;
     unsigned long long *wthr = thr + warp * TQ;
     int *wcnt = cnt + warp * TQ;
+    unsigned int tdist[TQ];      // distance part of each query's current k-th key (fast reject)
+#pragma unroll
+    for (int a = 0; a < TQ; ++a) tdist[a] = 0xffffffffu;
 
     for (int t = 0; t < n_tiles; ++t) {
-        mbar_wait(&bars[t % kStages], (unsigned int)((t / kStages) & 1));
-        const uint4 *st4 = reinterpret_cast<const uint4 *>(st + (size_t)(t % kStages) * tile_bytes);
+        const int s = t % STAGES;
+        mbar_wait(&full[s], (unsigned int)((t / STAGES) & 1));
+        const uint4 *st4 = reinterpret_cast<const uint4 *>(st + (size_t)s * tile_bytes);
         unsigned int acc[TQ][kTD];
 #pragma unroll
         for (int a = 0; a < TQ; ++a)
@@ -229,50 +265,62 @@ __global__ void __launch_bounds__(kWarps * 32, 1) l1_scan_kernel(const ScanParam
             for (int b = 0; b < kTD; ++b) acc[a][b] = 0u;
 #pragma unroll 2
         for (int c = 0; c < C; ++c) {
-            uint4 dv[kTD];
+            uint4 dv[kTD], qv[TQ];
 #pragma unroll
             for (int b = 0; b < kTD; ++b) dv[b] = st4[(b * C + c) * 32 + lane];
 #pragma unroll
-            for (int a = 0; a < TQ; ++a) {
-                const uint4 qv = qs4[a * C + c];
+            for (int a = 0; a < TQ; ++a) qv[a] = qs4[a * C + c];
+            // word-major order: TQ*kTD independent accumulators between two updates of the same one
 #pragma unroll
-                for (int b = 0; b < kTD; ++b) {
-                    unsigned int s = acc[a][b];
-                    s = sad4(qv.x, dv[b].x, s);
-                    s = sad4(qv.y, dv[b].y, s);
-                    s = sad4(qv.z, dv[b].z, s);
-                    s = sad4(qv.w, dv[b].w, s);
-                    acc[a][b] = s;
-                }
-            }
+            for (int a = 0; a < TQ; ++a)
+#pragma unroll
+                for (int b = 0; b < kTD; ++b) acc[a][b] = sad4(qv[a].x, dv[b].x, acc[a][b]);
+#pragma unroll
+            for (int a = 0; a < TQ; ++a)
+#pragma unroll
+                for (int b = 0; b < kTD; ++b) acc[a][b] = sad4(qv[a].y, dv[b].y, acc[a][b]);
+#pragma unroll
+            for (int a = 0; a < TQ; ++a)
+#pragma unroll
+                for (int b = 0; b < kTD; ++b) acc[a][b] = sad4(qv[a].z, dv[b].z, acc[a][b]);
+#pragma unroll
+            for (int a = 0; a < TQ; ++a)
+#pragma unroll
+                for (int b = 0; b < kTD; ++b) acc[a][b] = sad4(qv[a].w, dv[b].w, acc[a][b]);
         }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);     // this warp no longer reads the stage
+
         // ---- candidate filter (warp-private buffers: no CTA-level synchronisation) ----
+        bool hit = false;
+#pragma unroll
+        for (int a = 0; a < TQ; ++a)
+#pragma unroll
+            for (int b = 0; b < kTD; ++b) hit = hit || (acc[a][b] <= tdist[a]);
+        if (!__any_sync(0xffffffffu, hit)) continue;          // common case once thresholds are tight
         const long long gbase = g_begin + (long long)t * kTD;
 #pragma unroll
-        for (int b = 0; b < kTD; ++b) {
-            const long long id = (gbase + b) * 32 + lane;
-            const bool valid = (gbase + b) < g_end && id < p.n;
+        for (int a = 0; a < TQ; ++a) {
 #pragma unroll
-            for (int a = 0; a < TQ; ++a) {
+            for (int b = 0; b < kTD; ++b) {
+                const long long id = (gbase + b) * 32 + lane;
+                const bool valid = (gbase + b) < g_end && id < p.n;
                 const unsigned long long key = ((unsigned long long)acc[a][b] << kIdBits) | (unsigned long long)id;
                 const bool pass = valid && key < wthr[a];
                 const unsigned int vote = __ballot_sync(0xffffffffu, pass);
                 if (vote) {
                     int cn = wcnt[a];
-                    if (cn + 32 > p.cap) {
-                        cn = warp_refine(wbuf + (size_t)a * p.cap, cn, p.cap, p.k, lane, &wthr[a]);
-                    }
-                    // the threshold may have tightened: keys that no longer pass are still
-                    // harmless (they sort behind the k-th key), so the vote is used as is
+                    if (cn + 32 > p.cap) cn = warp_refine(wbuf + (size_t)a * p.cap, cn, p.cap, p.k, lane, &wthr[a]);
+                    // keys that stopped passing after a refine are harmless: they sort behind the k-th key
                     if (pass) wbuf[(size_t)a * p.cap + cn + __popc(vote & ((1u << lane) - 1u))] = key;
                     __syncwarp();
                     if (lane == 0) wcnt[a] = cn + __popc(vote);
                     __syncwarp();
                 }
             }
+            const unsigned long long th = wthr[a];
+            tdist[a] = (th == kKeyMax) ? 0xffffffffu : (unsigned int)(th >> kIdBits);
         }
-        __syncthreads();   // every warp is done reading this stage
-        if (tid == 0 && t + kStages < n_tiles) issue(t + kStages);
     }
 
     // ---- final: sort each query's candidates and publish the k best keys of this split ----
@@ -367,7 +415,7 @@ __global__ void pair_scores_kernel(const int8_t *__restrict__ fps, int d, const 
 // host-side configuration shared by workspace_bytes and topk
 // ------------------------------------------------------------------------------------------
 struct ScanConfig {
-    int tq, td, cap;
+    int tq, td, stages, cap;
     long long n_qtiles, n_groups, splits, groups_per_split;
     size_t smem;
 };
@@ -380,28 +428,41 @@ bool make_config(long long nq, long long n, int d, int k, ScanConfig *cfg) {
     if (k > 480) { cap = 1024; tq = 1; }
     while (tq > 1 && (long long)kWarps * (tq / 2) >= nq) tq /= 2;   // few queries: smaller tiles
     const int dpad = chunks_of(d) * 16;
-    int td = kTDmax;
-    auto smem_of = [&](int tq_, int td_) {
+    int td = kTDmax, stages = kStagesMax;
+    auto smem_of = [&](int tq_, int td_, int st_) {
         const size_t qt = (size_t)kWarps * tq_;
-        return (size_t)128 + qt * dpad + (size_t)kStages * td_ * 32 * dpad + qt * cap * 8 + qt * 12 + 64;
+        return (size_t)128 + qt * dpad + (size_t)st_ * td_ * 32 * dpad + qt * cap * 8 + qt * 12 + 64;
     };
-    if (smem_of(1, td) > 227 * 1024) td = 1;            // wide vectors: one group per stage
-    while (tq > 1 && smem_of(tq, td) > 227 * 1024) tq /= 2;
-    if (smem_of(tq, td) > 227 * 1024) return false;
+    const size_t lim = 227 * 1024;
+    if (smem_of(1, td, stages) > lim) { td = 1; stages = 2; }      // wide vectors
+    while (tq > 1 && smem_of(tq, td, stages) > lim) tq /= 2;
+    if (smem_of(tq, td, stages) > lim) return false;
     const int kTD = td;
     cfg->tq = tq;
     cfg->td = td;
+    cfg->stages = stages;
     cfg->cap = cap;
-    cfg->smem = smem_of(tq, td);
+    cfg->smem = smem_of(tq, td, stages);
     cfg->n_qtiles = (nq + (long long)kWarps * tq - 1) / ((long long)kWarps * tq);
     cfg->n_groups = (n + 31) / 32;
-    const long long tiles = (cfg->n_groups + kTD - 1) / kTD;
-    // enough CTAs for ~4 waves of 148 SMs, but at least 8 tiles per split so that the
-    // per-split warm-up of the candidate buffers stays small
-    long long splits = (148 * 4 + cfg->n_qtiles - 1) / std::max<long long>(1, cfg->n_qtiles);
-    splits = std::max<long long>(1, std::min<long long>(splits, std::max<long long>(1, tiles / 8)));
-    splits = std::min<long long>(splits, 1024);
-    long long tiles_per_split = (tiles + splits - 1) / splits;
+    const long long tiles = std::max<long long>(1, (cfg->n_groups + kTD - 1) / kTD);
+    // One CTA per SM is resident (shared memory), so pick the number of database splits that fills
+    // whole waves of 148 CTAs: the smallest count (>= 1 wave, >= 8 tiles per split so the per-split
+    // warm-up of the candidate buffers stays small) whose last wave is >= 96 % full, else the fullest.
+    const long long sms = 148;
+    const long long s_max = std::max<long long>(1, std::min<long long>(1024, tiles / 8));
+    const long long s_min = std::min(s_max, std::max<long long>(1, (sms + cfg->n_qtiles - 1) / cfg->n_qtiles));
+    long long best_s = s_min;
+    double best_eff = -1.0;
+    for (long long sp = s_min; sp <= std::min(s_max, s_min + 4 * sms); ++sp) {
+        const long long tps = (tiles + sp - 1) / sp;
+        const long long real = (tiles + tps - 1) / tps;            // splits actually launched
+        const double waves = (double)(real * cfg->n_qtiles) / (double)sms;
+        const double eff = waves / (double)((long long)(waves + 0.999999));
+        if (eff > best_eff + 1e-9) { best_eff = eff; best_s = sp; }
+        if (eff >= 0.96) { best_s = sp; break; }
+    }
+    const long long tiles_per_split = (tiles + best_s - 1) / best_s;
     cfg->groups_per_split = tiles_per_split * kTD;
     cfg->splits = (cfg->n_groups + cfg->groups_per_split - 1) / std::max<long long>(1, cfg->groups_per_split);
     if (cfg->splits < 1) cfg->splits = 1;
@@ -483,21 +544,21 @@ int dctd_l1_topk(const int8_t *d_q, int64_t nq, const void *d_packed, int64_t n,
         void (*fn)(const ScanParams) = nullptr;
         if (cfg.td == kTDmax) {
             switch (cfg.tq) {
-                case 1: fn = l1_scan_kernel<1, kTDmax>; break;
-                case 2: fn = l1_scan_kernel<2, kTDmax>; break;
-                case 4: fn = l1_scan_kernel<4, kTDmax>; break;
-                default: fn = l1_scan_kernel<8, kTDmax>; break;
+                case 1: fn = l1_scan_kernel<1, kTDmax, kStagesMax>; break;
+                case 2: fn = l1_scan_kernel<2, kTDmax, kStagesMax>; break;
+                case 4: fn = l1_scan_kernel<4, kTDmax, kStagesMax>; break;
+                default: fn = l1_scan_kernel<8, kTDmax, kStagesMax>; break;
             }
         } else {
             switch (cfg.tq) {
-                case 1: fn = l1_scan_kernel<1, 1>; break;
-                case 2: fn = l1_scan_kernel<2, 1>; break;
-                case 4: fn = l1_scan_kernel<4, 1>; break;
-                default: fn = l1_scan_kernel<8, 1>; break;
+                case 1: fn = l1_scan_kernel<1, 1, 2>; break;
+                case 2: fn = l1_scan_kernel<2, 1, 2>; break;
+                case 4: fn = l1_scan_kernel<4, 1, 2>; break;
+                default: fn = l1_scan_kernel<8, 1, 2>; break;
             }
         }
         DCTD_CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem));
-        fn<<<grid, kWarps * 32, cfg.smem, stream>>>(sp);
+        fn<<<grid, (kWarps + 1) * 32, cfg.smem, stream>>>(sp);
         DCTD_LAUNCH_CHECK();
         mp.key_parts = sp.parts;
         mp.parts = (int)cfg.splits;

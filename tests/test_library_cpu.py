@@ -90,3 +90,15 @@ def test_no_oracle_import_in_product():
             if f.endswith(('.py', '.cu', '.cuh', '.h')):
                 text = open(os.path.join(dirpath, f)).read()
                 assert 'import oracle' not in text and 'from oracle' not in text, f
+
+
+def test_topk_workspace_sizes_host_logic(lib):
+    """dctd_l1_topk_workspace_bytes runs the same host-side configuration as dctd_l1_topk: exercise the
+    edge cases (empty / tiny databases, k and d limits) without a GPU."""
+    for nq, n in [(1, 0), (3, 1), (13, 43), (1, 10 ** 6), (8192, 10 ** 6), (32768, 5 * 10 ** 7), (100, 5000)]:
+        for k in (1, 50, 300, 992):
+            assert lib.dctd_l1_topk_workspace_bytes(nq, n, 480, k) >= nq * k * 8
+    assert lib.dctd_l1_topk_workspace_bytes(8, 1000, 480, 993) == 0      # k limit
+    assert lib.dctd_l1_topk_workspace_bytes(8, 1000, 4096, 10) == 0      # d limit
+    assert lib.dctd_l1_topk_workspace_bytes(8, 1000, 1024, 10) > 0       # wide vectors: one group per stage
+    assert lib.dctd_l1_packed_bytes(33, 480) == 64 * 480 and lib.dctd_l1_packed_bytes(1, 100) == 32 * 112
