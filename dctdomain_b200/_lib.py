@@ -67,7 +67,10 @@ def lib():
         'dctd_fp_execute': (C.c_int, [vp, vp, i64, vp, i64, vp, sz, u32, vp]),
         'dctd_fp_set_variant': (C.c_int, [C.c_int]),
         'dctd_fp_plan_dump': (C.c_int, [vp, vp, i64, vp, i64, C.POINTER(i64), C.POINTER(i64)]),
+        'dctd_scale_f64': (C.c_int, [vp, i64, vp, vp]),
+        'dctd_idct_quant_f64': (C.c_int, [vp, i32, i32, i32, vp, vp]),
         'dctd_l1_packed_bytes': (sz, [i64, i32]),
+        'dctd_l1_set_mode': (C.c_int, [C.c_int]),
         'dctd_l1_pack': (C.c_int, [vp, i64, i32, i64, vp, vp]),
         'dctd_l1_unpack': (C.c_int, [vp, i64, i32, vp, vp]),
         'dctd_l1_topk_workspace_bytes': (sz, [i64, i64, i32, i32]),

@@ -175,29 +175,133 @@ __device__ __forceinline__ unsigned int sad4(unsigned int a, unsigned int b, uns
     return r;
 }
 
-// ------------------------------------------------------------------------------------------
-// scan kernel
-// ------------------------------------------------------------------------------------------
-struct ScanParams {
-    const int8_t *q;            // [nq, d] row-major
-    const uint4 *packed;        // packed database
-    unsigned long long *parts;  // [S, nq, k] sorted keys per database split
-    long long nq, n;
-    int d, k, cap;
-    long long n_groups, groups_per_split;
-};
-
 __device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-// Warp-specialised scan: warp kWarps is the TMA producer (one elected lane), warps 0..kWarps-1 compute.
-// Stages are handed over with full/empty mbarriers, so compute warps never meet at a CTA barrier and
-// drift apart: while one warp filters candidates, the others keep the integer pipe busy.
+// bitonic merge of a bitonic sequence of `cap` keys (first half ascending, second half descending)
+__device__ __forceinline__ void warp_bitonic_merge(unsigned long long *buf, int cap, int lane) {
+    for (int j = cap >> 1; j > 0; j >>= 1) {
+        for (int i = lane; i < (cap >> 1); i += 32) {
+            const int lo = ((i & ~(j - 1)) << 1) | (i & (j - 1));
+            const int hi = lo | j;
+            const unsigned long long a = buf[lo], b = buf[hi];
+            if (a > b) { buf[lo] = b; buf[hi] = a; }
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// TMA-staged, warp-specialised SAD scan shared by the two scan kernels
+//   warp NW is the producer (one elected lane issues cp.async.bulk), warps 0..NW-1 compute;
+//   stages are handed over with full/empty mbarriers so compute warps never meet at a CTA barrier.
+// ------------------------------------------------------------------------------------------
+struct ScanParams {
+    const int8_t *q;            // [nq, d] row-major
+    const uint4 *packed;        // packed database
+    long long nq, n;
+    int d, k;
+    long long n_groups;         // groups visited (virtual index v; real group = v * gstride)
+    long long gstride;          // 1 = every group, s = every s-th group (threshold sample)
+    long long groups_per_split;
+    const int *qflags;          // optional [nq]: only query tiles with a flagged query are processed
+    // heap mode (l1_scan_kernel)
+    unsigned long long *parts;  // [S, nq, k] sorted keys per database split
+    int cap;
+    // threshold mode (l1_thresh_scan_kernel / l1_thresh_stream_kernel)
+    const unsigned long long *thr_keys;   // [nq, k] sorted keys of the sample: thr = thr_keys[q*k + k-1]
+    unsigned long long *cand;   // [nq, cmax] candidate keys
+    int *cnt;                   // [nq] candidates appended (may exceed cmax: overflow)
+    int cmax;
+};
+
+template <int NW, int TQ>
+__device__ __forceinline__ void load_queries(const ScanParams &p, unsigned char *qs, long long q0, int dpad) {
+    constexpr int QT = NW * TQ;
+    // biased by 0x80; zero-distance padding beyond d / nq
+    for (int i = threadIdx.x; i < QT * dpad; i += blockDim.x) {
+        const int qi = i / dpad, col = i % dpad;
+        unsigned char b = 0x80;
+        if (q0 + qi < p.nq && col < p.d) b = (unsigned char)p.q[(q0 + qi) * p.d + col] ^ 0x80;
+        qs[i] = b;
+    }
+}
+
+template <int kTD, int STAGES>
+__device__ __forceinline__ void producer_loop(const ScanParams &p, unsigned long long *full, unsigned long long *empty,
+                                              unsigned char *st, int tile_bytes, int C, int dpad,
+                                              long long g_begin, long long g_end, int n_tiles) {
+    for (int t = 0; t < n_tiles; ++t) {
+        const int s = t % STAGES;
+        if (t >= STAGES) mbar_wait_backoff(&empty[s], (unsigned int)(((t / STAGES) - 1) & 1));
+        const long long v = g_begin + (long long)t * kTD;
+        const int ng = (int)min((long long)kTD, g_end - v);
+        const unsigned int gbytes = 32u * (unsigned int)dpad;
+        mbar_expect_tx(&full[s], (unsigned int)ng * gbytes);
+        if (p.gstride == 1) {
+            bulk_g2s(st + (size_t)s * tile_bytes, p.packed + v * C * 32, (unsigned int)ng * gbytes, &full[s]);
+        } else {
+            for (int b = 0; b < ng; ++b)
+                bulk_g2s(st + (size_t)s * tile_bytes + (size_t)b * gbytes, p.packed + (v + b) * p.gstride * C * 32,
+                         gbytes, &full[s]);
+        }
+    }
+}
+
+// distances of this warp's TQ queries against lane's vector of each of the kTD groups of one stage
+template <int TQ, int kTD>
+__device__ __forceinline__ void sad_tile(const uint4 *st4, const uint4 *qs4, int C, int lane,
+                                         unsigned int (&acc)[TQ][kTD]) {
+#pragma unroll
+    for (int a = 0; a < TQ; ++a)
+#pragma unroll
+        for (int b = 0; b < kTD; ++b) acc[a][b] = 0u;
+#pragma unroll 2
+    for (int c = 0; c < C; ++c) {
+        uint4 dv[kTD], qv[TQ];
+#pragma unroll
+        for (int b = 0; b < kTD; ++b) dv[b] = st4[(b * C + c) * 32 + lane];
+#pragma unroll
+        for (int a = 0; a < TQ; ++a) qv[a] = qs4[a * C + c];
+        // word-major order: TQ*kTD independent accumulators between two updates of the same one
+#pragma unroll
+        for (int a = 0; a < TQ; ++a)
+#pragma unroll
+            for (int b = 0; b < kTD; ++b) acc[a][b] = sad4(qv[a].x, dv[b].x, acc[a][b]);
+#pragma unroll
+        for (int a = 0; a < TQ; ++a)
+#pragma unroll
+            for (int b = 0; b < kTD; ++b) acc[a][b] = sad4(qv[a].y, dv[b].y, acc[a][b]);
+#pragma unroll
+        for (int a = 0; a < TQ; ++a)
+#pragma unroll
+            for (int b = 0; b < kTD; ++b) acc[a][b] = sad4(qv[a].z, dv[b].z, acc[a][b]);
+#pragma unroll
+        for (int a = 0; a < TQ; ++a)
+#pragma unroll
+            for (int b = 0; b < kTD; ++b) acc[a][b] = sad4(qv[a].w, dv[b].w, acc[a][b]);
+    }
+}
+
+__device__ __forceinline__ bool tile_has_flag(const ScanParams &p, long long q0, int QT, int *s_any) {
+    if (threadIdx.x == 0) *s_any = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < QT; i += blockDim.x)
+        if (q0 + i < p.nq && p.qflags[q0 + i]) *s_any = 1;
+    __syncthreads();
+    return *s_any != 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// heap scan: exact top-k with warp-private candidate buffers (any database size; also computes the
+// threshold sample and the fallback for queries whose candidate list overflowed)
+// ------------------------------------------------------------------------------------------
 template <int TQ, int kTD, int STAGES>
 __global__ void __launch_bounds__((kWarps + 1) * 32, 1) l1_scan_kernel(const ScanParams p) {
     constexpr int QT = kWarps * TQ;
     extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ int s_any;
     const int C = chunks_of(p.d);
     const int dpad = C * 16;
     const int tile_bytes = kTD * 32 * dpad;
@@ -211,6 +315,7 @@ __global__ void __launch_bounds__((kWarps + 1) * 32, 1) l1_scan_kernel(const Sca
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long long q0 = (long long)blockIdx.y * QT;
+    if (p.qflags && !tile_has_flag(p, q0, QT, &s_any)) return;
     const long long g_begin = (long long)blockIdx.x * p.groups_per_split;
     const long long g_end = min(p.n_groups, g_begin + p.groups_per_split);
     const int n_tiles = (int)((g_end - g_begin + kTD - 1) / kTD);
@@ -219,33 +324,15 @@ __global__ void __launch_bounds__((kWarps + 1) * 32, 1) l1_scan_kernel(const Sca
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    // queries -> shared memory, biased by 0x80, zero-distance padding beyond d / nq
-    for (int i = tid; i < QT * dpad; i += blockDim.x) {
-        const int qi = i / dpad, col = i % dpad;
-        unsigned char b = 0x80;
-        if (q0 + qi < p.nq && col < p.d) b = (unsigned char)p.q[(q0 + qi) * p.d + col] ^ 0x80;
-        qs[i] = b;
-    }
+    load_queries<kWarps, TQ>(p, qs, q0, dpad);
     for (int i = tid; i < QT; i += blockDim.x) { thr[i] = kKeyMax; cnt[i] = 0; }
     __syncthreads();
 
     if (warp == kWarps) {
-        // ---------------- producer ----------------
-        if (lane == 0) {
-            for (int t = 0; t < n_tiles; ++t) {
-                const int s = t % STAGES;
-                if (t >= STAGES) mbar_wait_backoff(&empty[s], (unsigned int)(((t / STAGES) - 1) & 1));
-                const long long g = g_begin + (long long)t * kTD;
-                const int ng = (int)min((long long)kTD, g_end - g);
-                const unsigned int bytes = (unsigned int)ng * 32u * (unsigned int)dpad;
-                mbar_expect_tx(&full[s], bytes);
-                bulk_g2s(st + (size_t)s * tile_bytes, p.packed + g * C * 32, bytes, &full[s]);
-            }
-        }
+        if (lane == 0) producer_loop<kTD, STAGES>(p, full, empty, st, tile_bytes, C, dpad, g_begin, g_end, n_tiles);
         return;
     }
 
-    // ---------------- consumers ----------------
     const uint4 *qs4 = reinterpret_cast<const uint4 *>(qs) + (size_t)warp * TQ * C;
     unsigned long long *wbuf = buf + (size_t)warp * TQ * p.cap;
     unsigned long long *wthr = thr + warp * TQ;
@@ -257,37 +344,8 @@ __global__ void __launch_bounds__((kWarps + 1) * 32, 1) l1_scan_kernel(const Sca
     for (int t = 0; t < n_tiles; ++t) {
         const int s = t % STAGES;
         mbar_wait(&full[s], (unsigned int)((t / STAGES) & 1));
-        const uint4 *st4 = reinterpret_cast<const uint4 *>(st + (size_t)s * tile_bytes);
         unsigned int acc[TQ][kTD];
-#pragma unroll
-        for (int a = 0; a < TQ; ++a)
-#pragma unroll
-            for (int b = 0; b < kTD; ++b) acc[a][b] = 0u;
-#pragma unroll 2
-        for (int c = 0; c < C; ++c) {
-            uint4 dv[kTD], qv[TQ];
-#pragma unroll
-            for (int b = 0; b < kTD; ++b) dv[b] = st4[(b * C + c) * 32 + lane];
-#pragma unroll
-            for (int a = 0; a < TQ; ++a) qv[a] = qs4[a * C + c];
-            // word-major order: TQ*kTD independent accumulators between two updates of the same one
-#pragma unroll
-            for (int a = 0; a < TQ; ++a)
-#pragma unroll
-                for (int b = 0; b < kTD; ++b) acc[a][b] = sad4(qv[a].x, dv[b].x, acc[a][b]);
-#pragma unroll
-            for (int a = 0; a < TQ; ++a)
-#pragma unroll
-                for (int b = 0; b < kTD; ++b) acc[a][b] = sad4(qv[a].y, dv[b].y, acc[a][b]);
-#pragma unroll
-            for (int a = 0; a < TQ; ++a)
-#pragma unroll
-                for (int b = 0; b < kTD; ++b) acc[a][b] = sad4(qv[a].z, dv[b].z, acc[a][b]);
-#pragma unroll
-            for (int a = 0; a < TQ; ++a)
-#pragma unroll
-                for (int b = 0; b < kTD; ++b) acc[a][b] = sad4(qv[a].w, dv[b].w, acc[a][b]);
-        }
+        sad_tile<TQ, kTD>(reinterpret_cast<const uint4 *>(st + (size_t)s * tile_bytes), qs4, C, lane, acc);
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[s]);     // this warp no longer reads the stage
 
@@ -298,13 +356,13 @@ __global__ void __launch_bounds__((kWarps + 1) * 32, 1) l1_scan_kernel(const Sca
 #pragma unroll
             for (int b = 0; b < kTD; ++b) hit = hit || (acc[a][b] <= tdist[a]);
         if (!__any_sync(0xffffffffu, hit)) continue;          // common case once thresholds are tight
-        const long long gbase = g_begin + (long long)t * kTD;
+        const long long vbase = g_begin + (long long)t * kTD;
 #pragma unroll
         for (int a = 0; a < TQ; ++a) {
 #pragma unroll
             for (int b = 0; b < kTD; ++b) {
-                const long long id = (gbase + b) * 32 + lane;
-                const bool valid = (gbase + b) < g_end && id < p.n;
+                const long long id = (vbase + b) * p.gstride * 32 + lane;
+                const bool valid = (vbase + b) < g_end && id < p.n;
                 const unsigned long long key = ((unsigned long long)acc[a][b] << kIdBits) | (unsigned long long)id;
                 const bool pass = valid && key < wthr[a];
                 const unsigned int vote = __ballot_sync(0xffffffffu, pass);
@@ -336,18 +394,219 @@ __global__ void __launch_bounds__((kWarps + 1) * 32, 1) l1_scan_kernel(const Sca
 }
 
 // ------------------------------------------------------------------------------------------
-// merge kernel: `parts` sorted lists per query -> k best, converted to (float32, int64)
+// threshold scan: every vector whose distance is <= the query's threshold (k-th best of a sample of
+// the database, an upper bound of the true k-th best) is appended to the query's candidate list in
+// global memory.  No per-warp selection state: the scan is SADs + one compare per pair.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void append_candidates(const ScanParams &p, long long qi, bool pass,
+                                                  unsigned long long key, int lane) {
+    const unsigned int vote = __ballot_sync(0xffffffffu, pass);
+    if (!vote) return;
+    int base = 0;
+    if (lane == 0) base = atomicAdd(&p.cnt[qi], __popc(vote));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    const int slot = base + __popc(vote & ((1u << lane) - 1u));
+    if (pass && slot < p.cmax) p.cand[qi * p.cmax + slot] = key;
+}
+
+template <int NW, int TQ, int kTD, int STAGES>
+__global__ void __launch_bounds__((NW + 1) * 32, 1) l1_thresh_scan_kernel(const ScanParams p) {
+    constexpr int QT = NW * TQ;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int C = chunks_of(p.d);
+    const int dpad = C * 16;
+    const int tile_bytes = kTD * 32 * dpad;
+    unsigned long long *full = reinterpret_cast<unsigned long long *>(smem);
+    unsigned long long *empty = full + STAGES;
+    unsigned char *qs = smem + 128;
+    unsigned char *st = qs + (size_t)QT * dpad;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long q0 = (long long)blockIdx.y * QT;
+    const long long g_begin = (long long)blockIdx.x * p.groups_per_split;
+    const long long g_end = min(p.n_groups, g_begin + p.groups_per_split);
+    const int n_tiles = (int)((g_end - g_begin + kTD - 1) / kTD);
+
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], NW); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    load_queries<NW, TQ>(p, qs, q0, dpad);
+    __syncthreads();
+
+    if (warp == NW) {
+        if (lane == 0) producer_loop<kTD, STAGES>(p, full, empty, st, tile_bytes, C, dpad, g_begin, g_end, n_tiles);
+        return;
+    }
+    const uint4 *qs4 = reinterpret_cast<const uint4 *>(qs) + (size_t)warp * TQ * C;
+    unsigned int tdist[TQ];
+#pragma unroll
+    for (int a = 0; a < TQ; ++a) {
+        const long long qi = q0 + warp * TQ + a;
+        unsigned long long th = kKeyMax;
+        if (qi < p.nq) th = p.thr_keys[qi * p.k + p.k - 1];
+        tdist[a] = (qi < p.nq) ? ((th == kKeyMax) ? 0xffffffffu : (unsigned int)(th >> kIdBits)) : 0u;
+    }
+    for (int t = 0; t < n_tiles; ++t) {
+        const int s = t % STAGES;
+        mbar_wait(&full[s], (unsigned int)((t / STAGES) & 1));
+        unsigned int acc[TQ][kTD];
+        sad_tile<TQ, kTD>(reinterpret_cast<const uint4 *>(st + (size_t)s * tile_bytes), qs4, C, lane, acc);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);
+        bool hit = false;
+#pragma unroll
+        for (int a = 0; a < TQ; ++a)
+#pragma unroll
+            for (int b = 0; b < kTD; ++b) hit = hit || (acc[a][b] <= tdist[a]);
+        if (!__any_sync(0xffffffffu, hit)) continue;
+        const long long vbase = g_begin + (long long)t * kTD;
+#pragma unroll
+        for (int a = 0; a < TQ; ++a) {
+            const long long qi = q0 + warp * TQ + a;
+#pragma unroll
+            for (int b = 0; b < kTD; ++b) {
+                const long long id = (vbase + b) * 32 + lane;
+                const bool pass = (vbase + b) < g_end && id < p.n && qi < p.nq && acc[a][b] <= tdist[a];
+                append_candidates(p, qi, pass, ((unsigned long long)acc[a][b] << kIdBits) | (unsigned long long)id, lane);
+            }
+        }
+    }
+}
+
+// Few queries (nq <= TQ): HBM-bound streaming.  Each warp takes whole groups straight from global memory
+// (lane v reads vector v: every load instruction covers 512 contiguous bytes), no shared-memory staging.
+template <int TQ>
+__global__ void __launch_bounds__(128) l1_thresh_stream_kernel(const ScanParams p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int C = chunks_of(p.d);
+    const int dpad = C * 16;
+    unsigned char *qs = smem;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    load_queries<1, TQ>(p, qs, 0, dpad);
+    __syncthreads();
+    const uint4 *qs4 = reinterpret_cast<const uint4 *>(qs);
+    unsigned int tdist[TQ];
+#pragma unroll
+    for (int a = 0; a < TQ; ++a) {
+        unsigned long long th = kKeyMax;
+        if (a < p.nq) th = p.thr_keys[(long long)a * p.k + p.k - 1];
+        tdist[a] = (a < p.nq) ? ((th == kKeyMax) ? 0xffffffffu : (unsigned int)(th >> kIdBits)) : 0u;
+    }
+    constexpr int UC = 6;      // chunks in flight per lane
+    const long long W = (long long)gridDim.x * (blockDim.x >> 5);
+    for (long long g = (long long)blockIdx.x * (blockDim.x >> 5) + warp; g < p.n_groups; g += W) {
+        const uint4 *gp = p.packed + g * C * 32 + lane;
+        unsigned int acc[TQ];
+#pragma unroll
+        for (int a = 0; a < TQ; ++a) acc[a] = 0u;
+        for (int c0 = 0; c0 < C; c0 += UC) {
+            uint4 dv[UC];
+#pragma unroll
+            for (int u = 0; u < UC; ++u) {
+                dv[u] = make_uint4(0x80808080u, 0x80808080u, 0x80808080u, 0x80808080u);
+                if (c0 + u < C) {
+                    const uint4 *src = gp + (size_t)(c0 + u) * 32;
+                    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                                 : "=r"(dv[u].x), "=r"(dv[u].y), "=r"(dv[u].z), "=r"(dv[u].w)
+                                 : "l"(src));
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < UC; ++u) {
+                if (c0 + u < C) {
+#pragma unroll
+                    for (int a = 0; a < TQ; ++a) {
+                        const uint4 qv = qs4[a * C + c0 + u];
+                        unsigned int s = acc[a];
+                        s = sad4(qv.x, dv[u].x, s);
+                        s = sad4(qv.y, dv[u].y, s);
+                        s = sad4(qv.z, dv[u].z, s);
+                        s = sad4(qv.w, dv[u].w, s);
+                        acc[a] = s;
+                    }
+                }
+            }
+        }
+        const long long id = g * 32 + lane;
+        bool hit = false;
+#pragma unroll
+        for (int a = 0; a < TQ; ++a) hit = hit || (acc[a] <= tdist[a]);
+        if (!__any_sync(0xffffffffu, hit)) continue;
+#pragma unroll
+        for (int a = 0; a < TQ; ++a) {
+            const bool pass = id < p.n && a < p.nq && acc[a] <= tdist[a];
+            append_candidates(p, a, pass, ((unsigned long long)acc[a] << kIdBits) | (unsigned long long)id, lane);
+        }
+    }
+}
+
+// exact selection from a query's candidate list: CTA-wide bitonic sort of up to cmax keys in shared memory
+struct SelectParams {
+    const unsigned long long *cand;
+    const int *cnt;
+    int cmax, k;
+    long long nq, id_base;
+    float *dist;
+    long long *ids;
+    int *qflags;       // out: 1 if the query's list overflowed (its result comes from the heap scan instead)
+};
+
+__global__ void __launch_bounds__(256) l1_select_kernel(const SelectParams p) {
+    extern __shared__ __align__(16) unsigned long long keys[];
+    const long long qi = blockIdx.x;
+    const int m = p.cnt[qi];
+    if (m > p.cmax) {
+        if (threadIdx.x == 0) p.qflags[qi] = 1;
+        return;
+    }
+    if (threadIdx.x == 0) p.qflags[qi] = 0;
+    int P = 64;
+    while (P < m) P <<= 1;
+    for (int i = threadIdx.x; i < P; i += blockDim.x) keys[i] = (i < m) ? p.cand[qi * p.cmax + i] : kKeyMax;
+    __syncthreads();
+    for (int k2 = 2; k2 <= P; k2 <<= 1) {
+        for (int j = k2 >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < (P >> 1); i += blockDim.x) {
+                const int lo = ((i & ~(j - 1)) << 1) | (i & (j - 1));
+                const int hi = lo | j;
+                const bool up = (lo & k2) == 0;
+                const unsigned long long a = keys[lo], b = keys[hi];
+                if ((a > b) == up) { keys[lo] = b; keys[hi] = a; }
+            }
+            __syncthreads();
+        }
+    }
+    for (int i = threadIdx.x; i < p.k; i += blockDim.x) {
+        const unsigned long long key = (i < P) ? keys[i] : kKeyMax;
+        const long long o = qi * p.k + i;
+        if (key == kKeyMax) {
+            p.dist[o] = FLT_MAX;
+            p.ids[o] = -1;
+        } else {
+            p.dist[o] = (float)(unsigned int)(key >> kIdBits);
+            p.ids[o] = (long long)(key & kIdMask) + p.id_base;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// merge kernel: sorted lists of k keys per (part, query) -> k best.  One warp per (query, chunk of
+// `ppw` parts); each further list is folded in with a bitonic MERGE (log2(cap) steps), not a sort.
+// Hierarchical: grid.y chunks write intermediate key lists; the last level converts to (float32, int64).
 // ------------------------------------------------------------------------------------------
 struct MergeParams {
     const unsigned long long *key_parts;   // [parts, nq, k] or null
     const float *dist_parts;               // [parts, nq, k] (PAIRS input)
     const long long *id_parts;
-    int parts;
+    int parts, ppw;
     long long nq;
     int k, cap;                            // cap = power of two >= 2k
     long long id_base;
+    unsigned long long *key_out;           // [grid.y, nq, k] when not the last level (or keys wanted)
     float *dist;
     long long *ids;
+    const int *qflags;                     // optional: only flagged queries are written
 };
 
 template <bool PAIRS>
@@ -357,21 +616,29 @@ __global__ void __launch_bounds__(128) l1_merge_kernel(const MergeParams p) {
     unsigned long long *buf = reinterpret_cast<unsigned long long *>(smem) + (size_t)warp * p.cap;
     const long long qi = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
     if (qi >= p.nq) return;
+    if (p.qflags && !p.qflags[qi]) return;
+    const int p0 = blockIdx.y * p.ppw, p1 = min(p.parts, p0 + p.ppw);
+    const int hcap = p.cap >> 1;
     auto load = [&](int part, int i) -> unsigned long long {
+        if (i >= p.k) return kKeyMax;
         const long long o = ((long long)part * p.nq + qi) * p.k + i;
         if (!PAIRS) return p.key_parts[o];
         const long long id = p.id_parts[o];
         if (id < 0) return kKeyMax;
         return ((unsigned long long)(unsigned int)p.dist_parts[o] << kIdBits) | (unsigned long long)id;
     };
-    for (int i = lane; i < p.k; i += 32) buf[i] = load(0, i);
-    for (int s = 1; s < p.parts; ++s) {
-        for (int i = lane; i < p.k; i += 32) buf[p.k + i] = load(s, i);
-        for (int i = 2 * p.k + lane; i < p.cap; i += 32) buf[i] = kKeyMax;
+    for (int i = lane; i < hcap; i += 32) buf[i] = load(p0, i);
+    for (int s = p0 + 1; s < p1; ++s) {
+        for (int i = lane; i < hcap; i += 32) buf[p.cap - 1 - i] = load(s, i);   // reversed: bitonic sequence
         __syncwarp();
-        warp_sort(buf, p.cap, lane);
+        warp_bitonic_merge(buf, p.cap, lane);
     }
     __syncwarp();
+    if (p.key_out) {
+        unsigned long long *out = p.key_out + ((long long)blockIdx.y * p.nq + qi) * p.k;
+        for (int i = lane; i < p.k; i += 32) out[i] = buf[i];
+        return;
+    }
     for (int i = lane; i < p.k; i += 32) {
         const unsigned long long key = buf[i];
         const long long o = qi * p.k + i;
@@ -414,13 +681,38 @@ __global__ void pair_scores_kernel(const int8_t *__restrict__ fps, int d, const 
 // ------------------------------------------------------------------------------------------
 // host-side configuration shared by workspace_bytes and topk
 // ------------------------------------------------------------------------------------------
-struct ScanConfig {
+constexpr long long kSMs = 148;
+constexpr size_t kSmemLimit = 227 * 1024;
+
+struct ScanConfig {          // heap scan (l1_scan_kernel)
     int tq, td, stages, cap;
     long long n_qtiles, n_groups, splits, groups_per_split;
     size_t smem;
 };
 
-bool make_config(long long nq, long long n, int d, int k, ScanConfig *cfg) {
+// One CTA per SM is resident (shared memory), so pick the number of database splits that fills whole
+// waves of 148 CTAs: the smallest count (>= 1 wave, >= 8 tiles per split so per-split warm-up stays
+// small) whose last wave is >= 96 % full, else the fullest.
+void pick_splits(long long n_groups, int td, long long n_qtiles, long long *splits, long long *groups_per_split) {
+    const long long tiles = std::max<long long>(1, (n_groups + td - 1) / td);
+    const long long s_max = std::max<long long>(1, std::min<long long>(1024, tiles / 8));
+    const long long s_min = std::min(s_max, std::max<long long>(1, (kSMs + n_qtiles - 1) / n_qtiles));
+    long long best_s = s_min;
+    double best_eff = -1.0;
+    for (long long sp = s_min; sp <= std::min(s_max, s_min + 4 * kSMs); ++sp) {
+        const long long tps = (tiles + sp - 1) / sp;
+        const long long real = (tiles + tps - 1) / tps;
+        const double waves = (double)(real * n_qtiles) / (double)kSMs;
+        const double eff = waves / (double)((long long)(waves + 0.999999));
+        if (eff > best_eff + 1e-9) { best_eff = eff; best_s = sp; }
+        if (eff >= 0.96) { best_s = sp; break; }
+    }
+    const long long tiles_per_split = (tiles + best_s - 1) / best_s;
+    *groups_per_split = tiles_per_split * td;
+    *splits = std::max<long long>(1, (n_groups + *groups_per_split - 1) / *groups_per_split);
+}
+
+bool make_config(long long nq, long long n_groups, int d, int k, ScanConfig *cfg) {
     if (k < 1 || k > 992 || d < 1 || d > 2048) return false;
     int cap = 128, tq = 8;
     if (k > 96) { cap = 256; tq = 4; }
@@ -433,39 +725,88 @@ bool make_config(long long nq, long long n, int d, int k, ScanConfig *cfg) {
         const size_t qt = (size_t)kWarps * tq_;
         return (size_t)128 + qt * dpad + (size_t)st_ * td_ * 32 * dpad + qt * cap * 8 + qt * 12 + 64;
     };
-    const size_t lim = 227 * 1024;
-    if (smem_of(1, td, stages) > lim) { td = 1; stages = 2; }      // wide vectors
-    while (tq > 1 && smem_of(tq, td, stages) > lim) tq /= 2;
-    if (smem_of(tq, td, stages) > lim) return false;
-    const int kTD = td;
-    cfg->tq = tq;
-    cfg->td = td;
-    cfg->stages = stages;
-    cfg->cap = cap;
+    if (smem_of(1, td, stages) > kSmemLimit) { td = 1; stages = 2; }      // wide vectors
+    while (tq > 1 && smem_of(tq, td, stages) > kSmemLimit) tq /= 2;
+    if (smem_of(tq, td, stages) > kSmemLimit) return false;
+    cfg->tq = tq; cfg->td = td; cfg->stages = stages; cfg->cap = cap;
     cfg->smem = smem_of(tq, td, stages);
     cfg->n_qtiles = (nq + (long long)kWarps * tq - 1) / ((long long)kWarps * tq);
-    cfg->n_groups = (n + 31) / 32;
-    const long long tiles = std::max<long long>(1, (cfg->n_groups + kTD - 1) / kTD);
-    // One CTA per SM is resident (shared memory), so pick the number of database splits that fills
-    // whole waves of 148 CTAs: the smallest count (>= 1 wave, >= 8 tiles per split so the per-split
-    // warm-up of the candidate buffers stays small) whose last wave is >= 96 % full, else the fullest.
-    const long long sms = 148;
-    const long long s_max = std::max<long long>(1, std::min<long long>(1024, tiles / 8));
-    const long long s_min = std::min(s_max, std::max<long long>(1, (sms + cfg->n_qtiles - 1) / cfg->n_qtiles));
-    long long best_s = s_min;
-    double best_eff = -1.0;
-    for (long long sp = s_min; sp <= std::min(s_max, s_min + 4 * sms); ++sp) {
-        const long long tps = (tiles + sp - 1) / sp;
-        const long long real = (tiles + tps - 1) / tps;            // splits actually launched
-        const double waves = (double)(real * cfg->n_qtiles) / (double)sms;
-        const double eff = waves / (double)((long long)(waves + 0.999999));
-        if (eff > best_eff + 1e-9) { best_eff = eff; best_s = sp; }
-        if (eff >= 0.96) { best_s = sp; break; }
+    cfg->n_groups = n_groups;
+    pick_splits(n_groups, td, cfg->n_qtiles, &cfg->splits, &cfg->groups_per_split);
+    return true;
+}
+
+struct ThreshConfig {        // threshold scan (l1_thresh_scan_kernel / l1_thresh_stream_kernel)
+    bool stream;
+    int nw, tq;              // compute warps per CTA, queries per warp (stream: tq = queries per pass)
+    long long n_qtiles, splits, groups_per_split;
+    size_t smem;
+};
+
+struct TopkPlan {
+    bool thresh;
+    ScanConfig full;         // heap scan of the whole database: the only scan when !thresh, else the fallback
+    ScanConfig samp;         // heap scan of the sample that sets the thresholds
+    long long gstride;
+    ThreshConfig tc;
+    int cmax;
+    size_t off_parts_full, off_parts_samp, off_tmp, off_thr, off_cnt, off_flags, off_cand, total;
+};
+
+constexpr int kCmax = 8192;  // candidate slots per query (threshold path)
+constexpr int kMergePPW = 32;
+
+bool make_plan(long long nq, long long n, int d, int k, TopkPlan *pl) {
+    const long long n_groups = (n + 31) / 32;
+    if (!make_config(nq, n_groups, d, k, &pl->full)) return false;
+    pl->thresh = false;
+    pl->cmax = kCmax;
+    const int dpad = chunks_of(d) * 16;
+    // threshold path: large databases, moderate k (the sample must stay a small fraction of the database
+    // while the expected candidate count k * gstride stays well below cmax)
+    const long long gs = std::min<long long>(32, (kCmax / 4) / std::max(1, k));
+    if (n >= 65536 && gs >= 8 && pl->full.td == kTDmax) {
+        pl->gstride = gs;
+        const long long sg = (n_groups + gs - 1) / gs;
+        ThreshConfig tc{};
+        if (nq <= 16) {
+            tc.stream = true;
+            tc.nw = 4;
+            tc.tq = nq <= 4 ? 4 : (nq <= 8 ? 8 : 16);
+            tc.n_qtiles = 1;
+            tc.smem = (size_t)tc.tq * dpad;
+        } else {
+            tc.stream = false;
+            tc.nw = nq >= 1024 ? 16 : 8;
+            tc.tq = 8;
+            while (tc.tq > 4 && (long long)tc.nw * (tc.tq / 2) >= nq) tc.tq /= 2;
+            const size_t qt = (size_t)tc.nw * tc.tq;
+            tc.smem = 128 + qt * dpad + (size_t)kStagesMax * kTDmax * 32 * dpad + 64;
+            tc.n_qtiles = (nq + (long long)qt - 1) / (long long)qt;
+            pick_splits(n_groups, kTDmax, tc.n_qtiles, &tc.splits, &tc.groups_per_split);
+        }
+        if (tc.smem <= kSmemLimit && make_config(nq, sg, d, k, &pl->samp)) {
+            pl->tc = tc;
+            pl->thresh = true;
+        }
     }
-    const long long tiles_per_split = (tiles + best_s - 1) / best_s;
-    cfg->groups_per_split = tiles_per_split * kTD;
-    cfg->splits = (cfg->n_groups + cfg->groups_per_split - 1) / std::max<long long>(1, cfg->groups_per_split);
-    if (cfg->splits < 1) cfg->splits = 1;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { const size_t o = off; off += dctd::align_up(bytes, 256); return o; };
+    const size_t list = (size_t)nq * (size_t)k * 8;
+    pl->off_parts_full = take((size_t)pl->full.splits * list);
+    size_t tmp_parts = pl->full.splits > kMergePPW ? (size_t)((pl->full.splits + kMergePPW - 1) / kMergePPW) : 0;
+    pl->off_parts_samp = pl->off_thr = pl->off_cnt = pl->off_flags = pl->off_cand = 0;
+    if (pl->thresh) {
+        pl->off_parts_samp = take((size_t)pl->samp.splits * list);
+        if (pl->samp.splits > kMergePPW)
+            tmp_parts = std::max(tmp_parts, (size_t)((pl->samp.splits + kMergePPW - 1) / kMergePPW));
+        pl->off_thr = take(list);
+        pl->off_cnt = take((size_t)nq * sizeof(int));
+        pl->off_flags = take((size_t)nq * sizeof(int));
+        pl->off_cand = take((size_t)nq * (size_t)pl->cmax * 8);
+    }
+    pl->off_tmp = take(tmp_parts * list);
+    pl->total = off + 256;
     return true;
 }
 
@@ -475,9 +816,70 @@ int next_pow2(int x) {
     return p;
 }
 
+typedef void (*ScanFn)(const ScanParams);
+
+ScanFn heap_kernel(const ScanConfig &c) {
+    if (c.td == kTDmax) {
+        switch (c.tq) {
+            case 1: return l1_scan_kernel<1, kTDmax, kStagesMax>;
+            case 2: return l1_scan_kernel<2, kTDmax, kStagesMax>;
+            case 4: return l1_scan_kernel<4, kTDmax, kStagesMax>;
+            default: return l1_scan_kernel<8, kTDmax, kStagesMax>;
+        }
+    }
+    switch (c.tq) {
+        case 1: return l1_scan_kernel<1, 1, 2>;
+        case 2: return l1_scan_kernel<2, 1, 2>;
+        case 4: return l1_scan_kernel<4, 1, 2>;
+        default: return l1_scan_kernel<8, 1, 2>;
+    }
+}
+
+int launch_heap(const ScanConfig &c, ScanParams sp, cudaStream_t stream) {
+    if (c.n_qtiles > 65535) return DCTD_ERR_UNSUPPORTED;   // caller batches queries
+    sp.cap = c.cap;
+    sp.n_groups = c.n_groups;
+    sp.groups_per_split = c.groups_per_split;
+    ScanFn fn = heap_kernel(c);
+    DCTD_CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem));
+    fn<<<dim3((unsigned)c.splits, (unsigned)c.n_qtiles), (kWarps + 1) * 32, c.smem, stream>>>(sp);
+    DCTD_LAUNCH_CHECK();
+    return DCTD_OK;
+}
+
+// folds `parts` sorted key lists per query; the result goes to (dist, ids) or, if key_out is given, stays keys
+int run_merge(const unsigned long long *keys, long long parts, long long nq, int k, long long id_base, float *dist,
+              long long *ids, unsigned long long *key_out, const int *qflags, unsigned long long *tmp,
+              cudaStream_t stream) {
+    MergeParams mp{};
+    mp.nq = nq; mp.k = k; mp.cap = next_pow2(2 * k); mp.id_base = id_base; mp.qflags = qflags;
+    const int warps = 4;
+    const size_t msmem = (size_t)warps * mp.cap * 8;
+    DCTD_CUDA_TRY(cudaFuncSetAttribute(l1_merge_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem));
+    const unsigned gx = (unsigned)((nq + warps - 1) / warps);
+    if (parts > kMergePPW) {
+        if (parts > (long long)kMergePPW * kMergePPW) return DCTD_ERR_UNSUPPORTED;
+        const long long chunks = (parts + kMergePPW - 1) / kMergePPW;
+        mp.key_parts = keys; mp.parts = (int)parts; mp.ppw = kMergePPW; mp.key_out = tmp;
+        l1_merge_kernel<false><<<dim3(gx, (unsigned)chunks), warps * 32, msmem, stream>>>(mp);
+        DCTD_LAUNCH_CHECK();
+        keys = tmp;
+        parts = chunks;
+    }
+    mp.key_parts = keys; mp.parts = (int)parts; mp.ppw = (int)parts; mp.key_out = key_out;
+    mp.dist = dist; mp.ids = ids;
+    l1_merge_kernel<false><<<dim3(gx, 1), warps * 32, msmem, stream>>>(mp);
+    DCTD_LAUNCH_CHECK();
+    return DCTD_OK;
+}
+
+int g_l1_mode = 0;   // tuning / test hook: 0 = automatic, 1 = force the heap scan, see dctd_l1_set_mode
+
 }  // namespace
 
 extern "C" {
+
+int dctd_l1_set_mode(int mode) { g_l1_mode = mode; return DCTD_OK; }
 
 size_t dctd_l1_packed_bytes(int64_t n, int32_t d) {
     if (n < 0 || d < 1) return 0;
@@ -507,9 +909,9 @@ int dctd_l1_unpack(const void *d_packed, int64_t n, int32_t d, int8_t *d_rows, v
 }
 
 size_t dctd_l1_topk_workspace_bytes(int64_t nq, int64_t n, int32_t d, int32_t k) {
-    ScanConfig cfg;
-    if (nq <= 0 || n < 0 || !make_config(nq, n, d, k, &cfg)) return 0;
-    return dctd::align_up((size_t)cfg.splits * (size_t)nq * (size_t)k * 8, 256) + 256;
+    TopkPlan pl;
+    if (nq <= 0 || n < 0 || !make_plan(nq, n, d, k, &pl)) return 0;
+    return pl.total;
 }
 
 int dctd_l1_topk(const int8_t *d_q, int64_t nq, const void *d_packed, int64_t n, int32_t d, int32_t k,
@@ -519,71 +921,108 @@ int dctd_l1_topk(const int8_t *d_q, int64_t nq, const void *d_packed, int64_t n,
     if (nq == 0) return DCTD_OK;
     if (!d_q || !d_dist || !d_ids || (n > 0 && !d_packed)) return DCTD_ERR_ARG;
     if (n >= (1LL << kIdBits)) return DCTD_ERR_UNSUPPORTED;
-    ScanConfig cfg;
-    if (!make_config(nq, n, d, k, &cfg)) return DCTD_ERR_UNSUPPORTED;
+    TopkPlan pl;
+    if (!make_plan(nq, n, d, k, &pl)) return DCTD_ERR_UNSUPPORTED;
     cudaStream_t stream = (cudaStream_t)stream_;
-    const size_t need = dctd_l1_topk_workspace_bytes(nq, n, d, k);
-    if (!d_workspace || workspace_bytes < need) return DCTD_ERR_WORKSPACE;
+    if (!d_workspace || workspace_bytes < pl.total) return DCTD_ERR_WORKSPACE;
     if (((uintptr_t)d_workspace & 255) != 0 || ((uintptr_t)d_packed & 15) != 0) return DCTD_ERR_ARG;
+    char *ws = (char *)d_workspace;
+    unsigned long long *parts_full = (unsigned long long *)(ws + pl.off_parts_full);
+    unsigned long long *tmp = (unsigned long long *)(ws + pl.off_tmp);
+    long long *ids = (long long *)d_ids;
 
-    MergeParams mp{};
-    mp.nq = nq; mp.k = k; mp.id_base = id_base; mp.dist = d_dist; mp.ids = (long long *)d_ids;
-    mp.cap = next_pow2(2 * k);
-    if (n == 0) {
-        // empty database: all slots are padding.  Reuse the merge kernel on one all-MAX part.
-        DCTD_CUDA_TRY(cudaMemsetAsync(d_workspace, 0xff, (size_t)nq * k * 8, stream));
-        mp.key_parts = (const unsigned long long *)d_workspace;
-        mp.parts = 1;
-    } else {
-        ScanParams sp{};
-        sp.q = d_q; sp.packed = (const uint4 *)d_packed; sp.parts = (unsigned long long *)d_workspace;
-        sp.nq = nq; sp.n = n; sp.d = d; sp.k = k; sp.cap = cfg.cap;
-        sp.n_groups = cfg.n_groups; sp.groups_per_split = cfg.groups_per_split;
-        if (cfg.n_qtiles > 65535) return DCTD_ERR_UNSUPPORTED;   // caller batches queries
-        dim3 grid((unsigned)cfg.splits, (unsigned)cfg.n_qtiles);
-        void (*fn)(const ScanParams) = nullptr;
-        if (cfg.td == kTDmax) {
-            switch (cfg.tq) {
-                case 1: fn = l1_scan_kernel<1, kTDmax, kStagesMax>; break;
-                case 2: fn = l1_scan_kernel<2, kTDmax, kStagesMax>; break;
-                case 4: fn = l1_scan_kernel<4, kTDmax, kStagesMax>; break;
-                default: fn = l1_scan_kernel<8, kTDmax, kStagesMax>; break;
-            }
-        } else {
-            switch (cfg.tq) {
-                case 1: fn = l1_scan_kernel<1, 1, 2>; break;
-                case 2: fn = l1_scan_kernel<2, 1, 2>; break;
-                case 4: fn = l1_scan_kernel<4, 1, 2>; break;
-                default: fn = l1_scan_kernel<8, 1, 2>; break;
-            }
-        }
-        DCTD_CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem));
-        fn<<<grid, (kWarps + 1) * 32, cfg.smem, stream>>>(sp);
-        DCTD_LAUNCH_CHECK();
-        mp.key_parts = sp.parts;
-        mp.parts = (int)cfg.splits;
+    if (n == 0) {   // empty database: every slot is padding
+        DCTD_CUDA_TRY(cudaMemsetAsync(parts_full, 0xff, (size_t)nq * k * 8, stream));
+        return run_merge(parts_full, 1, nq, k, id_base, d_dist, ids, nullptr, nullptr, tmp, stream);
     }
-    const int warps = 4;
-    const size_t msmem = (size_t)warps * mp.cap * 8;
-    DCTD_CUDA_TRY(cudaFuncSetAttribute(l1_merge_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem));
-    l1_merge_kernel<false><<<(unsigned)((nq + warps - 1) / warps), warps * 32, msmem, stream>>>(mp);
-    DCTD_LAUNCH_CHECK();
-    return DCTD_OK;
+    ScanParams sp{};
+    sp.q = d_q; sp.packed = (const uint4 *)d_packed; sp.nq = nq; sp.n = n; sp.d = d; sp.k = k; sp.gstride = 1;
+
+    if (!pl.thresh || g_l1_mode == 1) {
+        sp.parts = parts_full;
+        int rc = launch_heap(pl.full, sp, stream);
+        if (rc != DCTD_OK) return rc;
+        return run_merge(parts_full, pl.full.splits, nq, k, id_base, d_dist, ids, nullptr, nullptr, tmp, stream);
+    }
+
+    // ---- threshold path ----
+    unsigned long long *parts_samp = (unsigned long long *)(ws + pl.off_parts_samp);
+    unsigned long long *thr = (unsigned long long *)(ws + pl.off_thr);
+    int *cnt = (int *)(ws + pl.off_cnt);
+    int *flags = (int *)(ws + pl.off_flags);
+    unsigned long long *cand = (unsigned long long *)(ws + pl.off_cand);
+    // 1. thresholds: exact top-k of every gstride-th group
+    {
+        ScanParams s1 = sp;
+        s1.parts = parts_samp;
+        s1.gstride = pl.gstride;
+        int rc = launch_heap(pl.samp, s1, stream);
+        if (rc != DCTD_OK) return rc;
+        rc = run_merge(parts_samp, pl.samp.splits, nq, k, 0, nullptr, nullptr, thr, nullptr, tmp, stream);
+        if (rc != DCTD_OK) return rc;
+    }
+    // 2. one pass over the database: append everything within the threshold
+    DCTD_CUDA_TRY(cudaMemsetAsync(cnt, 0, (size_t)nq * sizeof(int), stream));
+    {
+        ScanParams s2 = sp;
+        s2.thr_keys = thr; s2.cand = cand; s2.cnt = cnt; s2.cmax = pl.cmax;
+        s2.n_groups = (n + 31) / 32;
+        const ThreshConfig &tc = pl.tc;
+        if (tc.stream) {
+            ScanFn fn = tc.tq == 4 ? l1_thresh_stream_kernel<4> : (tc.tq == 8 ? l1_thresh_stream_kernel<8> : l1_thresh_stream_kernel<16>);
+            int per_sm = 0;
+            DCTD_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, 128, tc.smem));
+            const long long want = std::max<long long>(1, (s2.n_groups + 3) / 4);
+            const int grid = (int)std::min<long long>(want, kSMs * std::max(1, per_sm));
+            fn<<<grid, 128, tc.smem, stream>>>(s2);
+            DCTD_LAUNCH_CHECK();
+        } else {
+            s2.groups_per_split = tc.groups_per_split;
+            ScanFn fn;
+            if (tc.nw == 16) fn = l1_thresh_scan_kernel<16, 8, kTDmax, kStagesMax>;
+            else if (tc.tq == 8) fn = l1_thresh_scan_kernel<8, 8, kTDmax, kStagesMax>;
+            else fn = l1_thresh_scan_kernel<8, 4, kTDmax, kStagesMax>;
+            if (tc.n_qtiles > 65535) return DCTD_ERR_UNSUPPORTED;
+            DCTD_CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc.smem));
+            fn<<<dim3((unsigned)tc.splits, (unsigned)tc.n_qtiles), (tc.nw + 1) * 32, tc.smem, stream>>>(s2);
+            DCTD_LAUNCH_CHECK();
+        }
+    }
+    // 3. exact selection per query; overflowed queries are flagged
+    {
+        SelectParams se{};
+        se.cand = cand; se.cnt = cnt; se.cmax = pl.cmax; se.k = k; se.nq = nq; se.id_base = id_base;
+        se.dist = d_dist; se.ids = ids; se.qflags = flags;
+        const size_t ssmem = (size_t)pl.cmax * 8;
+        DCTD_CUDA_TRY(cudaFuncSetAttribute(l1_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssmem));
+        l1_select_kernel<<<(unsigned)nq, 256, ssmem, stream>>>(se);
+        DCTD_LAUNCH_CHECK();
+    }
+    // 4. flagged queries (candidate list overflow: heavy distance ties, adversarial order) are redone by
+    //    the heap scan; CTAs of unflagged query tiles exit at once, so this costs a few microseconds
+    {
+        ScanParams s4 = sp;
+        s4.parts = parts_full;
+        s4.qflags = flags;
+        int rc = launch_heap(pl.full, s4, stream);
+        if (rc != DCTD_OK) return rc;
+        return run_merge(parts_full, pl.full.splits, nq, k, id_base, d_dist, ids, nullptr, flags, tmp, stream);
+    }
 }
 
 int dctd_l1_topk_merge(const float *d_dist_parts, const int64_t *d_ids_parts, int32_t parts, int64_t nq,
                        int32_t k, float *d_dist, int64_t *d_ids, void *stream) {
-    if (parts < 1 || nq < 0 || k < 1 || k > 1024) return DCTD_ERR_ARG;
+    if (parts < 1 || parts > 1024 || nq < 0 || k < 1 || k > 1024) return DCTD_ERR_ARG;
     if (nq == 0) return DCTD_OK;
     if (!d_dist_parts || !d_ids_parts || !d_dist || !d_ids) return DCTD_ERR_ARG;
     MergeParams mp{};
     mp.dist_parts = d_dist_parts; mp.id_parts = (const long long *)d_ids_parts;
-    mp.parts = parts; mp.nq = nq; mp.k = k; mp.cap = next_pow2(2 * k); mp.id_base = 0;
+    mp.parts = parts; mp.ppw = parts; mp.nq = nq; mp.k = k; mp.cap = next_pow2(2 * k); mp.id_base = 0;
     mp.dist = d_dist; mp.ids = (long long *)d_ids;
     const int warps = 4;
     const size_t msmem = (size_t)warps * mp.cap * 8;
     DCTD_CUDA_TRY(cudaFuncSetAttribute(l1_merge_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem));
-    l1_merge_kernel<true><<<(unsigned)((nq + warps - 1) / warps), warps * 32, msmem, (cudaStream_t)stream>>>(mp);
+    l1_merge_kernel<true><<<dim3((unsigned)((nq + warps - 1) / warps), 1), warps * 32, msmem, (cudaStream_t)stream>>>(mp);
     DCTD_LAUNCH_CHECK();
     return DCTD_OK;
 }

@@ -279,6 +279,33 @@ class Fingerprint:
         if len(domains) > 1:
             self.domains.append(f'1-{len(self.seq)}')
 
+    def scale(self, vec: np.ndarray) -> np.ndarray:
+        """(vec - min) / (max - min) over the whole array, float64 (src/fingerprint.py:110-123); on the GPU."""
+        dev = _device()
+        x = torch.from_numpy(np.ascontiguousarray(vec, dtype=np.float64)).to(dev)
+        out = torch.empty_like(x)
+        with torch.cuda.device(dev):
+            rc = _lib.lib().dctd_scale_f64(x.data_ptr(), x.numel(), out.data_ptr(),
+                                           torch.cuda.current_stream(dev).cuda_stream)
+        _lib.check(rc, 'dctd_scale_f64')
+        return out.cpu().numpy().reshape(np.shape(vec))
+
+    def idct_quant(self, vec: np.ndarray, num: int) -> np.ndarray:
+        """iDCTquant of src/fingerprint.py:126-142 for an arbitrary [rows, cols] matrix: DCT-II (ortho) along
+        the rows, first ``num`` coefficients, length-``num`` inverse, per-column min-max; returns
+        [num, cols] float64.  Runs on the GPU (dctd_idct_quant_f64); ``quantize`` does not call it - the
+        batched kernel fuses both passes."""
+        dev = _device()
+        x = torch.from_numpy(np.ascontiguousarray(vec, dtype=np.float64)).to(dev)
+        rows, cols = x.shape
+        n_out = min(int(num), rows)
+        out = torch.empty((n_out, cols), dtype=torch.float64, device=dev)
+        with torch.cuda.device(dev):
+            rc = _lib.lib().dctd_idct_quant_f64(x.data_ptr(), rows, cols, int(num), out.data_ptr(),
+                                                torch.cuda.current_stream(dev).cuda_stream)
+        _lib.check(rc, 'dctd_idct_quant_f64')
+        return out.cpu().numpy()
+
     def get_doms(self, embed, dom: str):
         """Rows of one domain, float64, in listed order, and the kept string (src/fingerprint.py:145-171)."""
         segs, kept = parse_domain(dom, embed.shape[0])

@@ -30,7 +30,7 @@ METRIC_L2 = 1
 METRIC_L1 = 2
 
 FLT_MAX = float(np.finfo(np.float32).max)
-_QUERY_BATCH = 32768
+_QUERY_BATCH = 8192     # queries per dctd_l1_topk call (bounds the candidate workspace: 64 KB per query)
 
 
 def _as_int8(x, d=None) -> np.ndarray:

@@ -99,6 +99,14 @@ int dctd_fp_execute(const dctd_fp_plan *plan, const void *const *h_src_ptrs, int
                     int8_t *d_out, int64_t out_stride, void *d_workspace, size_t workspace_bytes,
                     uint32_t flags, void *stream);
 
+/* The two small public helpers of reference src/fingerprint.py on arbitrary float64 matrices (device
+ * pointers): Fingerprint.scale (:110-123) over a whole vector, and Fingerprint.idct_quant (:126-142):
+ * d_x [rows, cols] row-major -> d_out [min(num, rows), cols].  Not tuned; quantize() itself is
+ * dctd_fp_execute. */
+int dctd_scale_f64(const double *d_x, int64_t n, double *d_out, void *stream);
+int dctd_idct_quant_f64(const double *d_x, int32_t rows, int32_t cols, int32_t num, double *d_out,
+                        void *stream);
+
 /* =====================================================================================
  * Hot path 2: exhaustive L1 top-k over int8 fingerprints
  *   replaces faiss.IndexFlat + METRIC_L1 search as called at reference src/query_db.py:75-76,87

@@ -162,3 +162,20 @@ def test_zz_write_parity_report():
     tot = [v for k, v in _stats.items() if k.split('/')[1] not in cases.ILL]
     rep['TOTAL_excluding_ill_conditioned'] = {'bytes_off_by_1': sum(v[0] for v in tot), 'bytes': sum(v[1] for v in tot)}
     json.dump(rep, open('gpurun_out/fingerprint_parity.json', 'w'), indent=1)
+
+
+def test_scale_and_idct_quant_helpers_match_reference_semantics():
+    """Fingerprint.scale / idct_quant (API surface of fingerprint.py:110-142) on the GPU vs the oracle."""
+    from dctdomain_b200.fingerprint import Fingerprint
+    fp = Fingerprint()
+    rs = np.random.RandomState(3)
+    v = rs.standard_normal(77)
+    assert np.allclose(fp.scale(v), fo.scale(v), rtol=0, atol=1e-15)
+    x = rs.standard_normal((150, 96))
+    a = fp.idct_quant(x, 3)
+    assert a.shape == (3, 96) and np.allclose(a, fo.idct_quant(x, 3), rtol=0, atol=1e-12)
+    b = fp.idct_quant(a.T, 80).T          # second call of quantize(): [96, 3] -> [80, 3] -> transposed
+    assert b.shape == (3, 80) and np.allclose(b, fo.idct_quant(fo.idct_quant(x, 3).T, 80).T, rtol=0, atol=1e-11)
+    q = (b.reshape(240) * 127).astype('int8')
+    want = fo.quant2d_matrix(x, 3, 80)
+    assert np.abs(q.astype(int) - want.astype(int)).max() <= 1

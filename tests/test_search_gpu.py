@@ -200,3 +200,45 @@ def test_properties_at_scale():
         best = torch.sort(key)[0][:50]
         assert np.array_equal((best % (1 << 32)).cpu().numpy(), im[qi])
         assert np.array_equal((best // (1 << 32)).cpu().numpy().astype(np.float32), dm[qi])
+
+
+# ---- large databases take the threshold path (sample -> thresholds -> one compaction pass -> select) ----
+@pytest.mark.parametrize('nq', [1, 4, 5, 13, 16, 17, 64, 300])
+def test_threshold_path_vs_oracle(nq):
+    db = synth.fingerprints(51, 100_000)
+    rs = np.random.RandomState(nq)
+    q = db[rs.choice(len(db), nq, replace=False)].copy()
+    q[::2] = np.clip(q[::2].astype(int) + rs.randint(-2, 3, size=q[::2].shape), 0, 127).astype(np.int8)
+    _check(q, db, 50)
+
+
+@pytest.mark.parametrize('k', [1, 10, 100, 256, 300])
+def test_threshold_path_k_values(k):
+    db = synth.fingerprints(52, 80_000)
+    _check(db[1000:1024], db, k)
+
+
+def test_threshold_path_overflow_falls_back_to_heap_scan():
+    """Massive distance ties make the candidate list overflow: those queries are redone by the heap scan."""
+    rs = np.random.RandomState(5)
+    db = rs.randint(0, 2, size=(70_000, 480)).astype(np.int8)
+    db[10_000:30_000] = db[3]                       # 20k exact duplicates of one vector
+    q = np.concatenate([db[:6], db[10_000:10_004], rs.randint(0, 2, size=(30, 480)).astype(np.int8)])
+    _check(q, db, 50)
+    _check(q[:7], db, 20)                           # streaming kernel + fallback
+
+
+def test_threshold_and_heap_paths_agree_at_scale():
+    from dctdomain_b200 import _lib
+    db = synth.fingerprints(53, 400_000)
+    idx = _index(db)
+    q = db[::4001][:100]
+    a = idx.search(q, 50)
+    _lib.lib().dctd_l1_set_mode(1)
+    try:
+        b = idx.search(q, 50)
+    finally:
+        _lib.lib().dctd_l1_set_mode(0)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    a = idx.search(q[:9], 50)
+    assert np.array_equal(a[0], b[0][:9]) and np.array_equal(a[1], b[1][:9])
