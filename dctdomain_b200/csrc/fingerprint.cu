@@ -323,7 +323,8 @@ __global__ void __launch_bounds__(MAXT, MINB) fp_kernel(const Params p) {
     __shared__ int s_bad[kMaxN];
 
     const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5;
-    const int D = p.D, m = p.m;
+    const int D = LDC ? LDC : p.D;      // specialised widths: D (= ld) is a compile-time constant
+    const int m = p.m;
     const int G = p.lay.G, RL = p.lay.RL, CT = p.lay.CT;
     const int nk = m - 1;
     const int DS = max(1, T / nk);
@@ -531,31 +532,43 @@ __global__ void __launch_bounds__(MAXT, MINB) fp_kernel(const Params p) {
             for (int j = 0; j < N; ++j) { f64[j] = 0.0; f32[j] = 0.f; }
             int d = d0;
             if constexpr (VEC == 4) {
-                int run = 0;
-                for (; d + 3 < d1; d += 4) {
+                // four columns per step: 16-byte shared loads of e / o, table offsets idx + {0,2k,4k,6k}
+                // (the table is extended by 8m entries, so only idx itself wraps)
+                const float *ye = Y + d0;                  // even k: e[d] at Y[j*D + d]
+                const float *yo = Y + D - 4 - d0;          // odd k : o[d] at Y[j*D + D-1-d] (reversed)
+                auto step4 = [&]() {
                     const float c0 = TT[idx], c1 = TT[idx + s1], c2 = TT[idx + s2], c3 = TT[idx + s3];
                     idx += s4;
                     while (idx >= 4 * D) idx -= 4 * D;
 #pragma unroll
                     for (int j = 0; j < N; ++j) {
-                        float4 v;
                         if (!odd) {
-                            v = *reinterpret_cast<const float4 *>(Y + j * D + d);
+                            const float4 v = *reinterpret_cast<const float4 *>(ye + j * D);
+                            f32[j] = fmaf(v.x, c0, f32[j]);
+                            f32[j] = fmaf(v.y, c1, f32[j]);
+                            f32[j] = fmaf(v.z, c2, f32[j]);
+                            f32[j] = fmaf(v.w, c3, f32[j]);
                         } else {
-                            const float4 t = *reinterpret_cast<const float4 *>(Y + j * D + D - 4 - d);
-                            v = make_float4(t.w, t.z, t.y, t.x);
+                            const float4 v = *reinterpret_cast<const float4 *>(yo + j * D);
+                            f32[j] = fmaf(v.w, c0, f32[j]);
+                            f32[j] = fmaf(v.z, c1, f32[j]);
+                            f32[j] = fmaf(v.y, c2, f32[j]);
+                            f32[j] = fmaf(v.x, c3, f32[j]);
                         }
-                        f32[j] = fmaf(v.x, c0, f32[j]);
-                        f32[j] = fmaf(v.y, c1, f32[j]);
-                        f32[j] = fmaf(v.z, c2, f32[j]);
-                        f32[j] = fmaf(v.w, c3, f32[j]);
                     }
-                    if (++run == 8) {       // float32 chains of 32 terms, then float64
+                    ye += 4;
+                    yo -= 4;
+                };
+                const int n4 = (d1 - d0) / 4;
+                int g = 0;
+                for (; g + 8 <= n4; g += 8) {               // float32 chains of 32 terms, then float64
 #pragma unroll
-                        for (int j = 0; j < N; ++j) { f64[j] += (double)f32[j]; f32[j] = 0.f; }
-                        run = 0;
-                    }
+                    for (int i = 0; i < 8; ++i) step4();
+#pragma unroll
+                    for (int j = 0; j < N; ++j) { f64[j] += (double)f32[j]; f32[j] = 0.f; }
                 }
+                for (; g < n4; ++g) step4();
+                d = d0 + 4 * n4;
             }
             for (; d < d1; ++d) {           // scalar path / leftovers
                 const float c = TT[idx];
