@@ -27,6 +27,20 @@ const char *dctd_strerror(int code) {
 int dctd_last_cuda_error(void) { return (int)dctd::g_last_cuda; }
 const char *dctd_last_cuda_error_string(void) { return cudaGetErrorString(dctd::g_last_cuda); }
 
+/* Host -> device staging for the Python surface: n independent copies (one cudaMemcpyAsync each, in order, on
+ * `stream`) of h_src[i] (nbytes[i] bytes, pinned or pageable) to d_base + d_off[i].  Saves the per-tensor
+ * interpreter overhead when a batch arrives as hundreds of separate host arrays. */
+int dctd_h2d_rows(const void *const *h_src, const int64_t *nbytes, int64_t n, void *d_base, const int64_t *d_off,
+                  void *stream) {
+    if (n < 0 || (n > 0 && (!h_src || !nbytes || !d_base || !d_off))) return DCTD_ERR_ARG;
+    for (int64_t i = 0; i < n; ++i) {
+        if (nbytes[i] == 0) continue;
+        DCTD_CUDA_TRY(cudaMemcpyAsync((char *)d_base + d_off[i], h_src[i], (size_t)nbytes[i], cudaMemcpyHostToDevice,
+                                      (cudaStream_t)stream));
+    }
+    return DCTD_OK;
+}
+
 int64_t dctd_launch_count(int reset) {
     int64_t v = dctd::g_launches;
     if (reset) dctd::g_launches = 0;

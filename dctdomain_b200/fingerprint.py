@@ -127,17 +127,24 @@ def execute_plan(plan: _Plan, src_tensors, out: torch.Tensor, tables_resident=Fa
     return out
 
 
-def _as_cuda(x, device):
-    """numpy / torch (cpu, pinned, cuda) [rows, D] -> contiguous float32 CUDA tensor."""
+def _host_f32(x):
+    """numpy / CPU torch [rows, D] -> (keep-alive object, address, rows, D) of contiguous float32 host memory."""
     if isinstance(x, torch.Tensor):
-        t = x
-    else:
-        t = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32))
-    if t.dtype != torch.float32:
-        t = t.to(torch.float32)
-    if t.device != device:
-        t = t.to(device, non_blocking=True)
-    return t.contiguous()
+        t = x if (x.dtype == torch.float32 and x.is_contiguous()) else x.to(torch.float32).contiguous()
+        return t, t.data_ptr(), int(t.shape[0]), int(t.shape[1])
+    a = np.ascontiguousarray(x, dtype=np.float32)
+    return a, a.ctypes.data, int(a.shape[0]), int(a.shape[1])
+
+
+_stage: dict = {}
+
+
+def _stage_buffer(device, nbytes):
+    buf = _stage.get(device)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(int(nbytes * 1.25) + (1 << 20), dtype=torch.uint8, device=device)
+        _stage[device] = buf
+    return buf
 
 
 def quantize_batch(fps, qdim=(3, 80, 3, 80), device=None, maxlen=DEFAULT_MAXLEN, overlap=OVERLAP):
@@ -145,7 +152,9 @@ def quantize_batch(fps, qdim=(3, 80, 3, 80), device=None, maxlen=DEFAULT_MAXLEN,
 
     Each object needs ``embed`` ({layer: [L, D] array | list of window arrays}), ``domains`` (list of
     RecCut strings) and ``quants`` (dict); they are updated exactly as the reference ``quantize`` does
-    (src/fingerprint.py:184-201).  Returns the list for convenience.
+    (src/fingerprint.py:184-201).  Host embeddings (numpy, CPU torch, pinned or not) are staged into one
+    device buffer with a single C call (one cudaMemcpyAsync per array); CUDA tensors are read in place.
+    Returns the list for convenience.
     """
     fps = list(fps)
     if not fps:
@@ -155,38 +164,100 @@ def quantize_batch(fps, qdim=(3, 80, 3, 80), device=None, maxlen=DEFAULT_MAXLEN,
     qdim = list(qdim)
     if len(qdim) < 2 * n_layers:
         raise IndexError('qdim needs an (n, m) pair per embedding layer')  # reference: list index error
-    for fp in fps:
-        if len(fp.embed) != n_layers:
-            raise ValueError('all proteins of a batch must carry the same layers')
+    L = _lib.lib()
 
-    # ---- sources (device residency) and geometry ----
-    src = [[] for _ in range(n_layers)]
+    # ---- sources: device pointer per (layer, source); host arrays are staged ----
+    ptr = [[] for _ in range(n_layers)]        # device addresses (staged ones are offsets until the copy)
+    staged = [[] for _ in range(n_layers)]     # True where ptr holds an offset into the staging buffer
+    keep, h_addr, h_bytes, h_off = [], [], [], []
     src_rows, prot_src0, prot_nsrc, prot_len = [], [], [], []
     D = None
-    for fp in fps:
+    stage_bytes = 0
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    have = _stage.get(dev)            # staging buffer of an earlier call (kept alive until this call returns)
+    state = {'done': 0, 'bases': []}  # bases: [(first h index, device address that h_off is relative to)]
+
+    def flush(final=False):
+        """Issues the H2D copies collected so far.  While the staging buffer of an earlier call is large enough
+        the copies start while the batch is still being walked (DMA overlaps the Python loop); whatever does not
+        fit goes to a buffer allocated once the total is known."""
+        lo = state['done']
+        if lo == len(h_addr):
+            return
+        if have is not None and stage_bytes <= have.numel():
+            base = have.data_ptr()
+            if not state['bases']:
+                state['bases'].append((0, base))
+        elif final:
+            first = h_off[lo]
+            base = _stage_buffer(dev, stage_bytes).data_ptr() - first     # remaining copies, rebased
+            state['bases'].append((lo, base))
+        else:
+            return
+        a_src = np.array(h_addr[lo:], dtype=np.uint64)
+        a_len = np.array(h_bytes[lo:], dtype=np.int64)
+        a_off = np.array(h_off[lo:], dtype=np.int64)
+        with torch.cuda.device(dev):
+            _lib.check(L.dctd_h2d_rows(a_src.ctypes.data, a_len.ctypes.data, len(a_src), base,
+                                       a_off.ctypes.data, stream), 'dctd_h2d_rows')
+        state['done'] = len(h_addr)
+
+    for fi, fp in enumerate(fps):
+        if fi % 32 == 31:
+            flush()
+        if len(fp.embed) != n_layers:
+            raise ValueError('all proteins of a batch must carry the same layers')
         layers = list(fp.embed.values())
-        wins0 = layers[0] if isinstance(layers[0], (list, tuple)) else [layers[0]]
+        nwin = len(layers[0]) if isinstance(layers[0], (list, tuple)) else 1
         prot_src0.append(len(src_rows))
-        prot_nsrc.append(len(wins0))
+        prot_nsrc.append(nwin)
+        rows0 = None
         for li, lay in enumerate(layers):
             wins = lay if isinstance(lay, (list, tuple)) else [lay]
-            if len(wins) != len(wins0):
+            if len(wins) != nwin:
                 raise ValueError(f'{fp.pid}: layers disagree on the number of windows')
+            rows = []
             for w in wins:
-                t = _as_cuda(w, dev)
-                if t.dim() != 2:
-                    raise ValueError('embeddings must be [rows, D]')
-                D = t.shape[1] if D is None else D
-                if t.shape[1] != D:
+                if isinstance(w, torch.Tensor) and w.is_cuda:
+                    t = w if (w.dtype == torch.float32 and w.is_contiguous() and w.device == dev) \
+                        else w.to(dev, torch.float32).contiguous()
+                    if t.dim() != 2:
+                        raise ValueError('embeddings must be [rows, D]')
+                    keep.append(t)
+                    r, dd = int(t.shape[0]), int(t.shape[1])
+                    ptr[li].append(t.data_ptr())
+                    staged[li].append(False)
+                else:
+                    if np.ndim(w) != 2:
+                        raise ValueError('embeddings must be [rows, D]')
+                    obj, addr, r, dd = _host_f32(w)
+                    keep.append(obj)
+                    h_addr.append(addr)
+                    h_bytes.append(r * dd * 4)
+                    h_off.append(stage_bytes)
+                    ptr[li].append(len(h_addr) - 1)       # index into h_*; resolved after the copies are issued
+                    staged[li].append(True)
+                    stage_bytes += (r * dd * 4 + 255) // 256 * 256
+                D = dd if D is None else D
+                if dd != D:
                     raise ValueError('all embeddings of a batch must share D')
-                src[li].append(t)
-        rows = [int(src[0][prot_src0[-1] + c].shape[0]) for c in range(len(wins0))]
-        for li in range(1, n_layers):
-            if [int(src[li][prot_src0[-1] + c].shape[0]) for c in range(len(wins0))] != rows:
+                rows.append(r)
+            if rows0 is None:
+                rows0 = rows
+            elif rows != rows0:
                 raise ValueError(f'{fp.pid}: layers disagree on the number of rows')
-        src_rows += rows
-        prot_len.append(rows[0] if len(rows) == 1 else (len(rows) - 1) * (maxlen - overlap) + rows[-1])
+        src_rows += rows0
+        prot_len.append(rows0[0] if nwin == 1 else (nwin - 1) * (maxlen - overlap) + rows0[-1])
 
+    flush(final=True)
+    if h_addr:
+        def resolve(hi):
+            base = state['bases'][-1][1] if hi >= state['bases'][-1][0] else state['bases'][0][1]
+            return base + h_off[hi]
+        for li in range(n_layers):
+            ptr[li] = [resolve(v) if st else v for v, st in zip(ptr[li], staged[li])]
+
+    # ---- domains ----
     dom_prot, dom_seg_off, seg_beg, seg_end, entries = [], [0], [], [], []
     for pi, fp in enumerate(fps):
         mine = []
@@ -203,33 +274,44 @@ def quantize_batch(fps, qdim=(3, 80, 3, 80), device=None, maxlen=DEFAULT_MAXLEN,
         entries.append(mine)
 
     # ---- one launch per distinct (n, m) (the reference call site uses one: [3, 80, 3, 80]) ----
-    blocks = []           # per layer: (tensor, column offset)
     groups: dict = {}
     for li in range(n_layers):
         groups.setdefault((int(qdim[2 * li]), int(qdim[2 * li + 1])), []).append(li)
-    outs = {}
+    blocks = [None] * n_layers       # per layer: int8 host array [n_dom, n*m]
     if dom_prot:
+        outs = []
         for (n, m), lids in groups.items():
             plan = make_plan(len(lids), D, n, m, src_rows, prot_src0, prot_nsrc, dom_prot, dom_seg_off,
                              seg_beg, seg_end, maxlen, overlap)
             out = torch.empty((len(dom_prot), len(lids) * n * m), dtype=torch.int8, device=dev)
-            execute_plan(plan, [src[li] for li in lids], out)
-            outs[(n, m)] = (out, lids)
-        host = {key: (o.cpu().numpy(), lids) for key, (o, lids) in outs.items()}
-        for li in range(n_layers):
-            key = (int(qdim[2 * li]), int(qdim[2 * li + 1]))
-            arr, lids = host[key]
-            nm = key[0] * key[1]
-            blocks.append(arr[:, lids.index(li) * nm:(lids.index(li) + 1) * nm])
+            ptrs = np.array([v for li in lids for v in ptr[li]], dtype=np.uint64)
+            ws = _workspace(dev, plan.workspace_bytes)
+            with torch.cuda.device(dev):
+                _lib.check(L.dctd_fp_execute(plan.handle, ptrs.ctypes.data, D, out.data_ptr(), out.stride(0),
+                                             ws.data_ptr(), ws.numel(), 0, stream), 'dctd_fp_execute')
+            outs.append((out, n * m, lids, plan))
+        for out, nm, lids, _plan in outs:
+            arr = out.cpu().numpy()
+            for pos, li in enumerate(lids):
+                blocks[li] = arr[:, pos * nm:(pos + 1) * nm]
 
     # ---- quants dicts, same update order as src/fingerprint.py:184-201 ----
     for pi, fp in enumerate(fps):
-        for li in range(n_layers):
-            for kept, row in entries[pi]:
-                fp.quants.setdefault(kept, []).extend(blocks[li][row].tolist())
-        for key, value in fp.quants.items():
-            fp.quants[key] = np.array(value)
+        mine = entries[pi]
+        simple = not fp.quants and len({kept for kept, _ in mine}) == len(mine)
+        if simple:      # the usual case: fresh object, every domain listed once
+            for kept, row in mine:
+                fp.quants[kept] = np.concatenate([blocks[li][row] for li in range(n_layers)]).astype(np.int64)
+        else:
+            for li in range(n_layers):
+                for kept, row in mine:
+                    fp.quants.setdefault(kept, []).extend(blocks[li][row].tolist())
+            for key, value in fp.quants.items():
+                fp.quants[key] = np.array(value)
         fp.domains = list(fp.quants.keys())
+    if not dom_prot and h_addr:
+        torch.cuda.current_stream(dev).synchronize()   # staged copies still read the host arrays
+    del keep
     return fps
 
 

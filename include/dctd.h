@@ -40,6 +40,12 @@ const char *dctd_last_cuda_error_string(void);
 /* number of kernel launches issued by this library on this thread since the last reset */
 int64_t dctd_launch_count(int reset);
 
+/* n host->device copies (one cudaMemcpyAsync each, in order, on `stream`): h_src[i] (nbytes[i] bytes, pinned or
+ * pageable host memory) -> d_base + d_off[i].  Used by the Python surface to stage a batch of host embeddings
+ * (the reference hands fingerprint.py numpy arrays, src/make_db.py:82) without per-array interpreter overhead. */
+int dctd_h2d_rows(const void *const *h_src, const int64_t *nbytes, int64_t n, void *d_base,
+                  const int64_t *d_off, void *stream);
+
 /* =====================================================================================
  * Hot path 1: DCT fingerprints ("quant2D")
  *   replaces reference src/fingerprint.py:110-201 (scale / idct_quant / get_doms / quantize)
