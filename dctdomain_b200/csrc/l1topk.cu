@@ -690,22 +690,23 @@ struct ScanConfig {          // heap scan (l1_scan_kernel)
     size_t smem;
 };
 
-// One CTA per SM is resident (shared memory), so pick the number of database splits that fills whole
-// waves of 148 CTAs: the smallest count (>= 1 wave, >= 8 tiles per split so per-split warm-up stays
-// small) whose last wave is >= 96 % full, else the fullest.
-void pick_splits(long long n_groups, int td, long long n_qtiles, long long *splits, long long *groups_per_split) {
+// One CTA per SM is resident (shared memory).  The number of database splits S trades whole waves of 148
+// CTAs against per-CTA fixed cost: time(S) ~ waves(S) * (tiles_per_split + overhead_tiles), where
+// overhead_tiles is the warm-up of a CTA expressed in tiles (heap scan: candidate buffers refine often
+// until the thresholds tighten, ~32 tiles' worth; threshold scan: just the query load).
+void pick_splits(long long n_groups, int td, long long n_qtiles, int overhead_tiles, long long *splits,
+                 long long *groups_per_split) {
     const long long tiles = std::max<long long>(1, (n_groups + td - 1) / td);
-    const long long s_max = std::max<long long>(1, std::min<long long>(1024, tiles / 8));
-    const long long s_min = std::min(s_max, std::max<long long>(1, (kSMs + n_qtiles - 1) / n_qtiles));
-    long long best_s = s_min;
-    double best_eff = -1.0;
-    for (long long sp = s_min; sp <= std::min(s_max, s_min + 4 * kSMs); ++sp) {
+    const long long s_max = std::max<long long>(1, std::min<long long>(1024, tiles / 4));
+    long long best_s = 1;
+    double best_cost = 1e300;
+    for (long long sp = 1; sp <= s_max; ++sp) {
         const long long tps = (tiles + sp - 1) / sp;
         const long long real = (tiles + tps - 1) / tps;
-        const double waves = (double)(real * n_qtiles) / (double)kSMs;
-        const double eff = waves / (double)((long long)(waves + 0.999999));
-        if (eff > best_eff + 1e-9) { best_eff = eff; best_s = sp; }
-        if (eff >= 0.96) { best_s = sp; break; }
+        const long long waves = (real * n_qtiles + kSMs - 1) / kSMs;
+        const double cost = (double)waves * (double)(tps + overhead_tiles);
+        if (cost < best_cost * 0.995) { best_cost = cost; best_s = sp; }
+        if (sp > 4 * kSMs && sp * n_qtiles > 16 * kSMs) break;
     }
     const long long tiles_per_split = (tiles + best_s - 1) / best_s;
     *groups_per_split = tiles_per_split * td;
@@ -732,7 +733,7 @@ bool make_config(long long nq, long long n_groups, int d, int k, ScanConfig *cfg
     cfg->smem = smem_of(tq, td, stages);
     cfg->n_qtiles = (nq + (long long)kWarps * tq - 1) / ((long long)kWarps * tq);
     cfg->n_groups = n_groups;
-    pick_splits(n_groups, td, cfg->n_qtiles, &cfg->splits, &cfg->groups_per_split);
+    pick_splits(n_groups, td, cfg->n_qtiles, 32, &cfg->splits, &cfg->groups_per_split);
     return true;
 }
 
@@ -783,7 +784,7 @@ bool make_plan(long long nq, long long n, int d, int k, TopkPlan *pl) {
             const size_t qt = (size_t)tc.nw * tc.tq;
             tc.smem = 128 + qt * dpad + (size_t)kStagesMax * kTDmax * 32 * dpad + 64;
             tc.n_qtiles = (nq + (long long)qt - 1) / (long long)qt;
-            pick_splits(n_groups, kTDmax, tc.n_qtiles, &tc.splits, &tc.groups_per_split);
+            pick_splits(n_groups, kTDmax, tc.n_qtiles, 2, &tc.splits, &tc.groups_per_split);
         }
         if (tc.smem <= kSmemLimit && make_config(nq, sg, d, k, &pl->samp)) {
             pl->tc = tc;
