@@ -645,6 +645,8 @@ __global__ void __launch_bounds__(MAXT, MINB) fp_kernel(const Params p) {
 // ------------------------------------------------------------------------------------------
 // host: layout, planner, launch
 // ------------------------------------------------------------------------------------------
+int g_variant = 0;   // tuning hook, see dctd_fp_set_variant
+
 Layout make_layout(int D, int n, int m, bool vec4) {
     Layout l{};
     const int K = n - 1;
@@ -652,7 +654,9 @@ Layout make_layout(int D, int n, int m, bool vec4) {
     l.G = (D + l.vec - 1) / l.vec;
     if (l.G <= kMaxThreads) {
         l.CT = 1;
-        l.RL = std::max(1, 320 / l.G);
+        // one thread per column group when that still fills >= 4 warps (more, smaller CTAs per SM overlap the
+        // non-streaming phases better); narrower embeddings share a CTA between several row lanes
+        l.RL = (l.G >= 128 && g_variant != 5) ? 1 : std::max(1, 320 / l.G);
         l.T = (l.G * l.RL + 31) / 32 * 32;
     } else {
         l.CT = (l.G + kMaxThreads - 1) / kMaxThreads;
@@ -675,7 +679,6 @@ Layout make_layout(int D, int n, int m, bool vec4) {
     return l;
 }
 
-int g_variant = 0;   // tuning hook, see dctd_fp_set_variant
 typedef void (*KernelFn)(const Params);
 template <int VEC, int U, int MAXT, int MINB>
 KernelFn pick_k(int K) {
@@ -927,6 +930,8 @@ int dctd_fp_execute(const dctd_fp_plan *plan, const void *const *h_src_ptrs, int
         else if (K == 2 && g_variant == 2) fn = fp_kernel<2, 4, 8, 320, 3>;
         else if (K == 2 && ld == plan->D && plan->D == 1280 && prm.lay.RL == 1) fn = fp_kernel<2, 4, 8, 320, 2, 1280, 1>;
         else if (K == 2 && ld == plan->D && plan->D == 640 && prm.lay.RL == 2) fn = fp_kernel<2, 4, 8, 320, 2, 640, 2>;
+        else if (K == 2 && ld == plan->D && plan->D == 640 && prm.lay.RL == 1) fn = fp_kernel<2, 4, 8, 160, 4, 640, 1>;
+        else if (K == 2 && ld == plan->D && plan->D == 1024 && prm.lay.RL == 1) fn = fp_kernel<2, 4, 8, 256, 2, 1024, 1>;
         else if (K == 2 && ld == plan->D && plan->D == 320 && prm.lay.RL == 4) fn = fp_kernel<2, 4, 8, 320, 2, 320, 4>;
         else fn = pick_k<4, 8, 320, 2>(K);
     } else if (K == 2 && ld == plan->D && plan->D == 2560 && prm.lay.RL == 1) fn = fp_kernel<2, 4, 8, kMaxThreads, 1, 2560, 1>;
