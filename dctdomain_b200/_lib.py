@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libdctd.so')
+LIB_PATH = os.environ.get('DCTD_LIB') or os.path.join(_HERE, 'libdctd.so')   # DCTD_LIB: e.g. the instrumented build
 
 OK = 0
 ERR_ARG, ERR_CUDA, ERR_WORKSPACE, ERR_UNSUPPORTED, ERR_NOMEM = -1, -2, -3, -4, -5
@@ -67,6 +67,8 @@ def lib():
         'dctd_fp_num_items': (i32, [vp]),
         'dctd_fp_execute': (C.c_int, [vp, vp, i64, vp, i64, vp, sz, u32, vp]),
         'dctd_fp_set_variant': (C.c_int, [C.c_int]),
+        'dctd_fp_set_fusion': (C.c_int, [C.c_int]),
+        'dctd_fp_timing_read': (C.c_int, [vp, vp, vp]),
         'dctd_fp_plan_dump': (C.c_int, [vp, vp, i64, vp, i64, C.POINTER(i64), C.POINTER(i64)]),
         'dctd_scale_f64': (C.c_int, [vp, i64, vp, vp]),
         'dctd_idct_quant_f64': (C.c_int, [vp, i32, i32, i32, vp, vp]),
@@ -79,8 +81,14 @@ def lib():
         'dctd_l1_topk_merge': (C.c_int, [vp, vp, i32, i64, i32, vp, vp, vp]),
         'dctd_l1_pair_scores': (C.c_int, [vp, i32, vp, vp, vp, i64, vp, vp, vp]),
     }
+    hooks = {'dctd_fp_set_variant', 'dctd_fp_set_fusion', 'dctd_fp_timing_read', 'dctd_fp_plan_dump', 'dctd_l1_set_mode'}
     for name, (res, args) in sig.items():
-        fn = getattr(L, name)          # AttributeError here = header / library mismatch
+        try:
+            fn = getattr(L, name)      # AttributeError here = header / library mismatch
+        except AttributeError:
+            if name in hooks:          # tuning / test hooks are not part of the ABI (older builds lack some)
+                continue
+            raise
         fn.restype = res
         fn.argtypes = args
     _lib = L

@@ -42,20 +42,23 @@ struct Piece {        // a run of consecutive domain rows read from one (or two 
     int32_t src_a, row_a;
     int32_t src_b, row_b;   // src_b < 0: single source
     int32_t nrows, l0;      // l0 = index of the first row within the concatenated domain
+    int32_t g0, pad;        // g0 = protein row of the first row (basis index of a riding global fingerprint)
 };
 struct DomInfo {
     int32_t piece_off, n_pieces;
     int32_t L;              // rows of the concatenated domain
     int32_t nsplit;
     int32_t slab0;          // first partial-sum slab (layer-major: slab0 + layer*nsplit + split)
-    int32_t counter0;       // arrival counter index base (counter0 + layer), -1 if nsplit == 1
-    int32_t pad0, pad1;
+    int32_t counter0;       // arrival counter index base (counter0 + layer), -1: the domain is one item
+    int32_t pivot;          // absolute index of the piece whose first row is the pivot
+    int32_t pad1;
 };
 struct Item {
     int32_t dom, layer;
     int32_t r0, r1;         // domain-local row range
     int32_t split, piece_first;
-    int32_t pad0, pad1;
+    int32_t rider_dom;      // >= 0: the global domain of the same protein accumulated from these rows too
+    int32_t rider_split;    // its partial-sum slot
 };
 
 struct Layout {             // thread / shared-memory layout derived from (D, n, m)
@@ -77,6 +80,7 @@ struct Params {
     const Item *items;
     int *counters;
     double *partials;
+    long long *timing;      // [16] phase cycle counters (DCTD_FP_TIMING builds only)
     int8_t *out;
     int64_t ld, out_stride;
     int32_t n_src, n_items, n_layers;
@@ -91,11 +95,12 @@ struct dctd_fp_plan {
     std::vector<Piece> pieces;
     std::vector<DomInfo> doms;
     std::vector<Item> items;
+    bool has_rider;           // some items carry their protein's global fingerprint along
     int32_t n_counters;       // 1 (work queue) + split arrival counters
     int64_t n_slabs;          // partial-sum slabs of (n-1)*D doubles
     int64_t algo_bytes;
     // device blob layout (bytes from the workspace base)
-    size_t off_pieces, off_doms, off_items, off_src, off_counters, off_table, off_partials, total;
+    size_t off_pieces, off_doms, off_items, off_src, off_counters, off_timing, off_table, off_partials, total;
     void *blob;               // host copy of [pieces | doms | items], pinned when possible
     bool blob_pinned;
     size_t blob_bytes;
@@ -142,29 +147,35 @@ __device__ __forceinline__ float ldg_stream1(const float *p) {
     return r;
 }
 
-// the K (c, c) pairs of one row; 16-byte shared loads when K is even
+// the K basis values of one row as (c, c) pairs (one FFMA2 covers two columns); vector shared loads when K allows.
+// The table holds plain floats: shared memory is the scarce resource here (what the CTAs do not take is L1,
+// and the L1 size bounds the loads in flight).
 template <int K>
-__device__ __forceinline__ void load_basis(const pk2 *p, pk2 (&c)[K]) {
-    if constexpr (K % 2 == 0) {
+__device__ __forceinline__ void load_basis(const float *p, pk2 (&c)[K]) {
+    if constexpr (K % 4 == 0) {
+#pragma unroll
+        for (int k = 0; k < K; k += 4) {
+            const float4 v = *reinterpret_cast<const float4 *>(p + k);
+            c[k] = pk(v.x, v.x); c[k + 1] = pk(v.y, v.y); c[k + 2] = pk(v.z, v.z); c[k + 3] = pk(v.w, v.w);
+        }
+    } else if constexpr (K % 2 == 0) {
 #pragma unroll
         for (int k = 0; k < K; k += 2) {
-            const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(p + k);
-            c[k] = v.x;
-            c[k + 1] = v.y;
+            const float2 v = *reinterpret_cast<const float2 *>(p + k);
+            c[k] = pk(v.x, v.x); c[k + 1] = pk(v.y, v.y);
         }
     } else {
 #pragma unroll
-        for (int k = 0; k < K; ++k) c[k] = p[k];
+        for (int k = 0; k < K; ++k) c[k] = pk(p[k], p[k]);
     }
 }
 
 // ---- pass 1, float4 path: rows rl, rl+RL, ... of one piece; acc[k] += (x - pivot) * c_k[row] ----
-// cb2[row*K + k] holds (c, c) so that one FFMA2 covers two columns.
 // LDC / RLC: compile-time row stride (floats) and row-lane count for the common ESM-2 widths (0 = runtime);
 // with them every load of a block is base + immediate and the address arithmetic disappears.
 template <int K, int U, bool DUAL, int LDC, int RLC>
 __device__ __forceinline__ void stream_piece4(const float *pa, const float *pb, int64_t ld_, int nr, int rl,
-                                              int RL_, const pk2 *cb2, pk2 npiv0, pk2 npiv1,
+                                              int RL_, const float *cb2, pk2 npiv0, pk2 npiv1,
                                               double (&acc)[K][4]) {
     const int RL = RLC ? RLC : RL_;
     const int64_t ld = LDC ? (int64_t)LDC : ld_;
@@ -173,7 +184,7 @@ __device__ __forceinline__ void stream_piece4(const float *pa, const float *pb, 
     const pk2 zero = pk(0.f, 0.f);
     pa += (int64_t)rl * ld;
     if (DUAL) pb += (int64_t)rl * ld;
-    const pk2 *cbp = cb2 + rl * K;
+    const float *cbp = cb2 + rl * K;
     const int cstep = RL * K;
     int left = (nr - rl + RL - 1) / RL;      // rows this thread owns
     if (left < 0) left = 0;
@@ -264,7 +275,7 @@ __device__ __forceinline__ void stream_piece4(const float *pa, const float *pb, 
 // ---- pass 1, scalar path (D % 4 != 0 or rows not 16-byte aligned) ----
 template <int K, bool DUAL>
 __device__ __forceinline__ void stream_piece1(const float *pa, const float *pb, int64_t ld, int nr, int rl,
-                                              int RL, const pk2 *cb2, float piv, double (&acc)[K][4]) {
+                                              int RL, const float *cb2, float piv, double (&acc)[K][4]) {
     constexpr int U = 8;
     for (int i0 = rl; i0 < nr; i0 += U * RL) {
         float x[U];
@@ -287,9 +298,7 @@ __device__ __forceinline__ void stream_piece1(const float *pa, const float *pb, 
                 const float t = x[u] - piv;
 #pragma unroll
                 for (int k = 0; k < K; ++k) {
-                    float c, c_;
-                    unpk(cb2[i * K + k], c, c_);
-                    a32[k] = fmaf(t, c, a32[k]);
+                    a32[k] = fmaf(t, cb2[i * K + k], a32[k]);
                 }
             }
         }
@@ -304,21 +313,41 @@ __global__ void fp_table_kernel(float *T, int D, int len) {
         T[i] = (float)cospi((double)(i % (4 * D)) / (2.0 * D));
 }
 
+// Optional per-phase cycle counters (build with -DDCTD_FP_TIMING; dctd_fp_timing_read): thread 0 of every CTA
+// accumulates clock64() deltas per phase into Params::timing.
+#ifdef DCTD_FP_TIMING
+#define TIC() long long _t0 = clock64()
+#define TOC(slot)                                                         \
+    do {                                                                  \
+        if (threadIdx.x == 0) {                                           \
+            const long long _t1 = clock64();                              \
+            atomicAdd((unsigned long long *)&p.timing[slot], (unsigned long long)(_t1 - _t0)); \
+            _t0 = _t1;                                                    \
+        }                                                                 \
+    } while (0)
+#else
+#define TIC() do {} while (0)
+#define TOC(slot) do {} while (0)
+#endif
+
 // ------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------
 // MAXT/MINB: launch bounds (registers per thread are capped at 65536 / (MAXT * MINB)).
-template <int K, int VEC, int U, int MAXT, int MINB, int LDC = 0, int RLC = 0>
+// RIDER: items of a protein's domains also accumulate the protein's global ("1-L") fingerprint from the
+// same loads (2K projections per element instead of K); the global's partial sums meet in the workspace.
+template <int K, int VEC, int U, int MAXT, int MINB, int LDC = 0, int RLC = 0, bool RIDER = false>
 __global__ void __launch_bounds__(MAXT, MINB) fp_kernel(const Params p) {
     constexpr int N = K + 1;
+    constexpr int KS = RIDER ? 2 * K : K;      // projections accumulated while streaming
     extern __shared__ __align__(16) unsigned char smem[];
     float *TT = reinterpret_cast<float *>(smem + p.lay.off_t4d);     // cos table (extended), pass 2a
     float *Y = reinterpret_cast<float *>(smem + p.lay.off_y);        // [N][D] pass-1 result, folded
-    pk2 *cb2 = reinterpret_cast<pk2 *>(smem + p.lay.off_cb);         // [rows][K] (c, c) basis of the item
-    double *scr = reinterpret_cast<double *>(smem + p.lay.off_scr);  // u sums, later F / Z
+    float *cb2 = reinterpret_cast<float *>(smem + p.lay.off_cb);     // [rows][KS] basis of the item
+    double *scr = reinterpret_cast<double *>(smem + p.lay.off_scr);  // u sums [KS][D], later F / Z
     double *Tm = reinterpret_cast<double *>(smem + p.lay.off_tm);    // cos(pi i / 2m), i < 4m
     double *Mj = reinterpret_cast<double *>(smem + p.lay.off_mj);    // [N][K] cos(pi (2j+1) k / 2n)
-    __shared__ int s_item, s_flag, s_last;
+    __shared__ int s_item, s_flag, s_last, s_last_rider;
     __shared__ double s_mn[kMaxN], s_mx[kMaxN];
     __shared__ int s_bad[kMaxN];
 
@@ -342,144 +371,11 @@ __global__ void __launch_bounds__(MAXT, MINB) fp_kernel(const Params p) {
     const int g0 = (RL > 1) ? tid % G : tid;
     const bool lane_ok = (RL > 1) ? (rl < RL) : true;
 
-    for (;;) {
+    // Everything after pass 1 for one (domain, layer) whose u[k][d] sums sit in scr[0 .. K*D).
+    auto finish = [&](int dom_index, int layer) {
+        TIC();
+        if (tid == 0) s_flag = 0;
         __syncthreads();
-        if (tid == 0) {
-            s_item = atomicAdd(&p.counters[0], 1);
-            s_flag = 0;
-        }
-        __syncthreads();
-        const int it = s_item;
-        if (it >= p.n_items) break;
-        const Item item = p.items[it];
-        const DomInfo dom = p.doms[item.dom];
-        const int L = dom.L, r0 = item.r0, r1 = item.r1;
-
-        // ---- basis of this item's rows: c_k = cos(pi (2l+1) k / 2L) by the Chebyshev recurrence
-        //      c_k = 2 c_1 c_{k-1} - c_{k-2} in float64 from one cospi per row ----
-        for (int r = tid; r < r1 - r0; r += T) {
-            const double c1 = cospi((double)(2 * (r0 + r) + 1) / (2.0 * L));
-            double ckm2 = 1.0, ckm1 = c1;
-            cb2[r * K] = pk((float)c1, (float)c1);
-#pragma unroll
-            for (int k = 2; k <= K; ++k) {
-                const double ck = 2.0 * c1 * ckm1 - ckm2;
-                cb2[r * K + k - 1] = pk((float)ck, (float)ck);
-                ckm2 = ckm1;
-                ckm1 = ck;
-            }
-        }
-        __syncthreads();
-
-        const float *const *src = p.src + (int64_t)item.layer * p.n_src;
-        const Piece first = p.pieces[dom.piece_off];
-        for (int ct = 0; ct < CT; ++ct) {
-            const int g = g0 + ct * T;
-            const bool active = lane_ok && g < G;
-            const int col = g * VEC;
-            double acc[K][4];
-#pragma unroll
-            for (int k = 0; k < K; ++k)
-#pragma unroll
-                for (int v = 0; v < 4; ++v) acc[k][v] = 0.0;
-            if (active) {
-                // pivot = row 0 of the domain (same for every split of the domain)
-                const float *fa = src[first.src_a] + (int64_t)first.row_a * p.ld + col;
-                const float *fb = (first.src_b >= 0) ? src[first.src_b] + (int64_t)first.row_b * p.ld + col : nullptr;
-                if constexpr (VEC == 4) {
-                    pk2 v0, v1;
-                    ldg_stream4(fa, v0, v1);
-                    if (fb) {
-                        pk2 w0, w1;
-                        ldg_stream4(fb, w0, w1);
-                        const pk2 hf = pk(0.5f, 0.5f);
-                        v0 = mul2(add2(v0, w0), hf);
-                        v1 = mul2(add2(v1, w1), hf);
-                    }
-                    const pk2 neg = pk(-1.f, -1.f);
-                    const pk2 npiv0 = mul2(v0, neg), npiv1 = mul2(v1, neg);
-                    for (int pi = item.piece_first; pi < dom.n_pieces; ++pi) {
-                        const Piece pc = p.pieces[dom.piece_off + pi];
-                        if (pc.l0 >= r1) break;
-                        const int a = max(pc.l0, r0), b = min(pc.l0 + pc.nrows, r1);
-                        if (a >= b) continue;
-                        const float *pa = src[pc.src_a] + (int64_t)(pc.row_a + (a - pc.l0)) * p.ld + col;
-                        const pk2 *cbp = cb2 + (a - r0) * K;
-                        if (pc.src_b < 0) {
-                            stream_piece4<K, U, false, LDC, RLC>(pa, pa, p.ld, b - a, rl, RL, cbp, npiv0, npiv1, acc);
-                        } else {
-                            const float *pb = src[pc.src_b] + (int64_t)(pc.row_b + (a - pc.l0)) * p.ld + col;
-                            stream_piece4<K, U, true, LDC, RLC>(pa, pb, p.ld, b - a, rl, RL, cbp, npiv0, npiv1, acc);
-                        }
-                    }
-                } else {
-                    float piv = ldg_stream1(fa);
-                    if (fb) piv = (piv + ldg_stream1(fb)) * 0.5f;
-                    for (int pi = item.piece_first; pi < dom.n_pieces; ++pi) {
-                        const Piece pc = p.pieces[dom.piece_off + pi];
-                        if (pc.l0 >= r1) break;
-                        const int a = max(pc.l0, r0), b = min(pc.l0 + pc.nrows, r1);
-                        if (a >= b) continue;
-                        const float *pa = src[pc.src_a] + (int64_t)(pc.row_a + (a - pc.l0)) * p.ld + col;
-                        const pk2 *cbp = cb2 + (a - r0) * K;
-                        if (pc.src_b < 0) {
-                            stream_piece1<K, false>(pa, pa, p.ld, b - a, rl, RL, cbp, piv, acc);
-                        } else {
-                            const float *pb = src[pc.src_b] + (int64_t)(pc.row_b + (a - pc.l0)) * p.ld + col;
-                            stream_piece1<K, true>(pa, pb, p.ld, b - a, rl, RL, cbp, piv, acc);
-                        }
-                    }
-                }
-            }
-            // ---- u[k][d] into shared memory, row lanes added in a fixed order ----
-            if (RL == 1) {
-                if (active) {
-#pragma unroll
-                    for (int k = 0; k < K; ++k)
-#pragma unroll
-                        for (int v = 0; v < VEC; ++v)
-                            if (col + v < D) scr[k * D + col + v] = acc[k][v];
-                }
-            } else {
-                for (int r = 0; r < RL; ++r) {
-                    if (active && rl == r) {
-#pragma unroll
-                        for (int k = 0; k < K; ++k)
-#pragma unroll
-                            for (int v = 0; v < VEC; ++v)
-                                if (col + v < D) {
-                                    if (r == 0) scr[k * D + col + v] = acc[k][v];
-                                    else scr[k * D + col + v] += acc[k][v];
-                                }
-                    }
-                    __syncthreads();
-                }
-            }
-        }
-        __syncthreads();
-
-        // ---- domains split over several items: partial sums meet in the workspace ----
-        if (dom.nsplit > 1) {
-            double *slab = p.partials + ((int64_t)dom.slab0 + (int64_t)item.layer * dom.nsplit) * (K * D);
-            double *mine = slab + (int64_t)item.split * (K * D);
-            for (int i = tid; i < K * D; i += T) mine[i] = scr[i];
-            __threadfence();
-            __syncthreads();
-            if (tid == 0) {
-                const int ticket = atomicAdd(&p.counters[dom.counter0 + item.layer], 1);
-                s_last = (ticket == dom.nsplit - 1);
-            }
-            __syncthreads();
-            if (!s_last) continue;
-            __threadfence();
-            for (int i = tid; i < K * D; i += T) {
-                double s = 0.0;
-                for (int sp = 0; sp < dom.nsplit; ++sp) s += __ldcg(slab + (int64_t)sp * (K * D) + i);
-                scr[i] = s;
-            }
-            __syncthreads();
-        }
-
         // ---- length-n inverse + per-column min-max (fingerprint.py:138-140 on [D, n]); Y = y' - 0.5 ----
         for (int d = tid; d < D; d += T) {
             double u[K], y[N];
@@ -504,6 +400,7 @@ __global__ void __launch_bounds__(MAXT, MINB) fp_kernel(const Params p) {
             for (int j = 0; j < N; ++j) Y[j * D + d] = (float)((y[j] - mn) * inv - 0.5);
         }
         __syncthreads();
+        TOC(8);
         // fold: cos(pi (2(D-1-d)+1) k / 2D) = (-1)^k cos(pi (2d+1) k / 2D), so even k only need
         // e[d] = Y[d] + Y[D-1-d] (kept at index d) and odd k only o[d] = Y[d] - Y[D-1-d] (at D-1-d)
         for (int i = tid; i < N * half; i += T) {
@@ -513,6 +410,7 @@ __global__ void __launch_bounds__(MAXT, MINB) fp_kernel(const Params p) {
             Y[j * D + D - 1 - d] = a - b;
         }
         __syncthreads();
+        TOC(9);
 
         // ---- pass 2a: F[j][k] = sum_{d < D/2} (e|o)[j][d] cos(pi (2d+1) k / 2D) (+ middle column) ----
         double *Fp = scr;                                  // [DS][N][nk]
@@ -532,32 +430,27 @@ __global__ void __launch_bounds__(MAXT, MINB) fp_kernel(const Params p) {
             for (int j = 0; j < N; ++j) { f64[j] = 0.0; f32[j] = 0.f; }
             int d = d0;
             if constexpr (VEC == 4) {
-                // four columns per step: 16-byte shared loads of e / o, table offsets idx + {0,2k,4k,6k}
-                // (the table is extended by 8m entries, so only idx itself wraps)
-                const float *ye = Y + d0;                  // even k: e[d] at Y[j*D + d]
-                const float *yo = Y + D - 4 - d0;          // odd k : o[d] at Y[j*D + D-1-d] (reversed)
+                // Four columns per step: one 16-byte shared load of e (even k, ascending from Y[j*D + d]) or
+                // o (odd k, stored reversed: o[d] at Y[j*D + D-1-d], so the float4 at D-4-d holds
+                // o[d+3..d]) and four table values at idx + {0,2k,4k,6k} (the table is extended by 8m entries,
+                // so only idx itself wraps).  For odd k the table offsets are taken in reverse order instead of
+                // reversing the vector: the loop body is the same for both parities, no divergence.
+                const float *yp = odd ? (Y + D - 4 - d0) : (Y + d0);
+                const int ystep = odd ? -4 : 4;
+                const int o0 = odd ? s3 : 0, o1 = odd ? s2 : s1, o2 = odd ? s1 : s2, o3 = odd ? 0 : s3;
                 auto step4 = [&]() {
-                    const float c0 = TT[idx], c1 = TT[idx + s1], c2 = TT[idx + s2], c3 = TT[idx + s3];
+                    const float c0 = TT[idx + o0], c1 = TT[idx + o1], c2 = TT[idx + o2], c3 = TT[idx + o3];
                     idx += s4;
                     while (idx >= 4 * D) idx -= 4 * D;
 #pragma unroll
                     for (int j = 0; j < N; ++j) {
-                        if (!odd) {
-                            const float4 v = *reinterpret_cast<const float4 *>(ye + j * D);
-                            f32[j] = fmaf(v.x, c0, f32[j]);
-                            f32[j] = fmaf(v.y, c1, f32[j]);
-                            f32[j] = fmaf(v.z, c2, f32[j]);
-                            f32[j] = fmaf(v.w, c3, f32[j]);
-                        } else {
-                            const float4 v = *reinterpret_cast<const float4 *>(yo + j * D);
-                            f32[j] = fmaf(v.w, c0, f32[j]);
-                            f32[j] = fmaf(v.z, c1, f32[j]);
-                            f32[j] = fmaf(v.y, c2, f32[j]);
-                            f32[j] = fmaf(v.x, c3, f32[j]);
-                        }
+                        const float4 v = *reinterpret_cast<const float4 *>(yp + j * D);
+                        f32[j] = fmaf(v.x, c0, f32[j]);
+                        f32[j] = fmaf(v.y, c1, f32[j]);
+                        f32[j] = fmaf(v.z, c2, f32[j]);
+                        f32[j] = fmaf(v.w, c3, f32[j]);
                     }
-                    ye += 4;
-                    yo -= 4;
+                    yp += ystep;
                 };
                 const int n4 = (d1 - d0) / 4;
                 int g = 0;
@@ -589,12 +482,14 @@ __global__ void __launch_bounds__(MAXT, MINB) fp_kernel(const Params p) {
             for (int j = 0; j < N; ++j) Fp[((size_t)ds * N + j) * nk + (k - 1)] = f64[j] + (double)f32[j];
         }
         __syncthreads();
+        TOC(10);
         for (int i = tid; i < N * nk; i += T) {
             double f = 0.0;
             for (int ds = 0; ds < DS; ++ds) f += Fp[(size_t)ds * N * nk + i];
             Fr[i] = f;
         }
         __syncthreads();
+        TOC(11);
 
         // ---- pass 2b: Z[j][c] = sum_k cos(pi (2c+1) k / 2m) F[j][k] ----
         for (int w = tid; w < N * m; w += T) {
@@ -611,6 +506,7 @@ __global__ void __launch_bounds__(MAXT, MINB) fp_kernel(const Params p) {
             Z[w] = z;
         }
         __syncthreads();
+        TOC(12);
 
         // ---- per-row min-max (one warp per row), *127, truncating int8 cast (fingerprint.py:193-195) ----
         for (int j = warp; j < N; j += (T >> 5)) {
@@ -631,14 +527,249 @@ __global__ void __launch_bounds__(MAXT, MINB) fp_kernel(const Params p) {
             if (lane == 0) { s_mn[j] = mn; s_mx[j] = mx; s_bad[j] = bad || !(mx > mn); }
         }
         __syncthreads();
+        TOC(13);
         const bool layer_bad = s_flag != 0;
-        int8_t *out = p.out + (int64_t)item.dom * p.out_stride + (int64_t)item.layer * (N * m);
+        int8_t *out = p.out + (int64_t)dom_index * p.out_stride + (int64_t)layer * (N * m);
         for (int w = tid; w < N * m; w += T) {
             const int j = w / m;
             int q = 0;
             if (!layer_bad && !s_bad[j]) q = (int)(((Z[w] - s_mn[j]) / (s_mx[j] - s_mn[j])) * 127.0);
             out[w] = (int8_t)q;
         }
+        __syncthreads();
+        TOC(14);
+    };
+
+    // publishes this item's partial sums (src[0 .. K*D) in shared memory) of a domain that is assembled
+    // from several items; returns true in the CTA that arrives last, with the total in scr[0 .. K*D)
+    auto meet = [&](const DomInfo &dm, int layer, int slot, const double *srcsum, int *s_result) -> bool {
+        double *slab = p.partials + ((int64_t)dm.slab0 + (int64_t)layer * dm.nsplit) * (K * D);
+        double *mine = slab + (int64_t)slot * (K * D);
+        for (int i = tid; i < K * D; i += T) mine[i] = srcsum[i];
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) {
+            const int ticket = atomicAdd(&p.counters[dm.counter0 + layer], 1);
+            *s_result = (ticket == dm.nsplit - 1);
+        }
+        __syncthreads();
+        if (!*s_result) return false;
+        __threadfence();
+        for (int i = tid; i < K * D; i += T) {
+            double s = 0.0;
+            for (int sp = 0; sp < dm.nsplit; ++sp) s += __ldcg(slab + (int64_t)sp * (K * D) + i);
+            scr[i] = s;
+        }
+        __syncthreads();
+        return true;
+    };
+
+    for (;;) {
+        TIC();
+        __syncthreads();
+        if (tid == 0) s_item = atomicAdd(&p.counters[0], 1);
+        __syncthreads();
+        const int it = s_item;
+        if (it >= p.n_items) break;
+        TOC(0);
+        const Item item = p.items[it];
+        const DomInfo dom = p.doms[item.dom];
+        const int L = dom.L, r0 = item.r0, r1 = item.r1;
+        const bool has_rider = RIDER && item.rider_dom >= 0;
+
+        // ---- basis of this item's rows: c_k = cos(pi (2l+1) k / 2L) by the Chebyshev recurrence
+        //      c_k = 2 c_1 c_{k-1} - c_{k-2} in float64 from one cospi per row ----
+        for (int r = tid; r < r1 - r0; r += T) {
+            const double c1 = cospi((double)(2 * (r0 + r) + 1) / (2.0 * L));
+            double ckm2 = 1.0, ckm1 = c1;
+            cb2[r * KS] = (float)c1;
+#pragma unroll
+            for (int k = 2; k <= K; ++k) {
+                const double ck = 2.0 * c1 * ckm1 - ckm2;
+                cb2[r * KS + k - 1] = (float)ck;
+                ckm2 = ckm1;
+                ckm1 = ck;
+            }
+            if constexpr (RIDER) {
+#pragma unroll
+                for (int k = 0; k < K; ++k) cb2[r * KS + K + k] = 0.f;
+            }
+        }
+        if constexpr (RIDER) {
+            if (has_rider) {
+                // second basis: the same rows at their position in the whole protein (the rider's own L)
+                __syncthreads();
+                const int Lg = p.doms[item.rider_dom].L;
+                for (int pi = item.piece_first; pi < dom.n_pieces; ++pi) {
+                    const Piece pc = p.pieces[dom.piece_off + pi];
+                    if (pc.l0 >= r1) break;
+                    const int a = max(pc.l0, r0), b = min(pc.l0 + pc.nrows, r1);
+                    for (int l = a + tid; l < b; l += T) {
+                        const int P = pc.g0 + (l - pc.l0);
+                        const double c1 = cospi((double)(2 * P + 1) / (2.0 * Lg));
+                        double ckm2 = 1.0, ckm1 = c1;
+                        cb2[(l - r0) * KS + K] = (float)c1;
+#pragma unroll
+                        for (int k = 2; k <= K; ++k) {
+                            const double ck = 2.0 * c1 * ckm1 - ckm2;
+                            cb2[(l - r0) * KS + K + k - 1] = (float)ck;
+                            ckm2 = ckm1;
+                            ckm1 = ck;
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        TOC(1);
+
+        const float *const *src = p.src + (int64_t)item.layer * p.n_src;
+        const Piece first = p.pieces[dom.pivot];
+        double *rider_slab = nullptr;
+        DomInfo gd{};
+        if constexpr (RIDER) {
+            if (has_rider) {
+                gd = p.doms[item.rider_dom];
+                rider_slab = p.partials + ((int64_t)gd.slab0 + (int64_t)item.layer * gd.nsplit + item.rider_split) * (K * D);
+            }
+        }
+        for (int ct = 0; ct < CT; ++ct) {
+            const int g = g0 + ct * T;
+            const bool active = lane_ok && g < G;
+            const int col = g * VEC;
+            double acc[KS][4];
+#pragma unroll
+            for (int k = 0; k < KS; ++k)
+#pragma unroll
+                for (int v = 0; v < 4; ++v) acc[k][v] = 0.0;
+            if (active) {
+                // pivot: one row subtracted from every row of the domain (row 0 of the domain, or of the
+                // protein when the global fingerprint rides along; the same for every item of a domain)
+                const float *fa = src[first.src_a] + (int64_t)first.row_a * p.ld + col;
+                const float *fb = (first.src_b >= 0) ? src[first.src_b] + (int64_t)first.row_b * p.ld + col : nullptr;
+                if constexpr (VEC == 4) {
+                    pk2 v0, v1;
+                    ldg_stream4(fa, v0, v1);
+                    if (fb) {
+                        pk2 w0, w1;
+                        ldg_stream4(fb, w0, w1);
+                        const pk2 hf = pk(0.5f, 0.5f);
+                        v0 = mul2(add2(v0, w0), hf);
+                        v1 = mul2(add2(v1, w1), hf);
+                    }
+                    const pk2 neg = pk(-1.f, -1.f);
+                    const pk2 npiv0 = mul2(v0, neg), npiv1 = mul2(v1, neg);
+                    for (int pi = item.piece_first; pi < dom.n_pieces; ++pi) {
+                        const Piece pc = p.pieces[dom.piece_off + pi];
+                        if (pc.l0 >= r1) break;
+                        const int a = max(pc.l0, r0), b = min(pc.l0 + pc.nrows, r1);
+                        if (a >= b) continue;
+                        const float *pa = src[pc.src_a] + (int64_t)(pc.row_a + (a - pc.l0)) * p.ld + col;
+                        const float *cbp = cb2 + (a - r0) * KS;
+                        if (pc.src_b < 0) {
+                            stream_piece4<KS, U, false, LDC, RLC>(pa, pa, p.ld, b - a, rl, RL, cbp, npiv0, npiv1, acc);
+                        } else {
+                            const float *pb = src[pc.src_b] + (int64_t)(pc.row_b + (a - pc.l0)) * p.ld + col;
+                            stream_piece4<KS, U, true, LDC, RLC>(pa, pb, p.ld, b - a, rl, RL, cbp, npiv0, npiv1, acc);
+                        }
+                    }
+                } else {
+                    float piv = ldg_stream1(fa);
+                    if (fb) piv = (piv + ldg_stream1(fb)) * 0.5f;
+                    for (int pi = item.piece_first; pi < dom.n_pieces; ++pi) {
+                        const Piece pc = p.pieces[dom.piece_off + pi];
+                        if (pc.l0 >= r1) break;
+                        const int a = max(pc.l0, r0), b = min(pc.l0 + pc.nrows, r1);
+                        if (a >= b) continue;
+                        const float *pa = src[pc.src_a] + (int64_t)(pc.row_a + (a - pc.l0)) * p.ld + col;
+                        const float *cbp = cb2 + (a - r0) * KS;
+                        if (pc.src_b < 0) {
+                            stream_piece1<KS, false>(pa, pa, p.ld, b - a, rl, RL, cbp, piv, acc);
+                        } else {
+                            const float *pb = src[pc.src_b] + (int64_t)(pc.row_b + (a - pc.l0)) * p.ld + col;
+                            stream_piece1<KS, true>(pa, pb, p.ld, b - a, rl, RL, cbp, piv, acc);
+                        }
+                    }
+                }
+            }
+            // ---- u[k][d] into shared memory, row lanes added in a fixed order ----
+            if (RL == 1) {
+                if (active) {
+#pragma unroll
+                    for (int k = 0; k < K; ++k)
+#pragma unroll
+                        for (int v = 0; v < VEC; ++v)
+                            if (col + v < D) scr[k * D + col + v] = acc[k][v];
+                    if constexpr (RIDER) {
+                        if (has_rider) {       // the rider's sums go straight to its partial-sum slab
+#pragma unroll
+                            for (int k = 0; k < K; ++k)
+#pragma unroll
+                                for (int v = 0; v < VEC; ++v)
+                                    if (col + v < D) rider_slab[k * D + col + v] = acc[K + k][v];
+                        }
+                    }
+                }
+            } else {
+                for (int r = 0; r < RL; ++r) {
+                    if (active && rl == r) {
+#pragma unroll
+                        for (int k = 0; k < KS; ++k)
+#pragma unroll
+                            for (int v = 0; v < VEC; ++v)
+                                if (col + v < D) {
+                                    if (r == 0) scr[k * D + col + v] = acc[k][v];
+                                    else scr[k * D + col + v] += acc[k][v];
+                                }
+                    }
+                    __syncthreads();
+                }
+            }
+        }
+        __syncthreads();
+        TOC(2);
+
+        // ---- the protein's global fingerprint riding on this item: hand its partial sums over ----
+        bool rider_last = false;
+        if constexpr (RIDER) {
+            if (has_rider) {
+                // with row lanes the rider's sums were reduced in scr[K*D .. 2*K*D) (the item's own sums in
+                // scr[0 .. K*D) stay untouched); with one thread per column group they are already in the slab
+                if (RL > 1)
+                    for (int i = tid; i < K * D; i += T) rider_slab[i] = scr[K * D + i];
+                __threadfence();
+                __syncthreads();
+                if (tid == 0) {
+                    const int ticket = atomicAdd(&p.counters[gd.counter0 + item.layer], 1);
+                    s_last_rider = (ticket == gd.nsplit - 1);
+                }
+                __syncthreads();
+                rider_last = s_last_rider != 0;
+            }
+        }
+
+        TOC(3);
+        // ---- this item's own domain ----
+        bool own_ready = true;
+        if (dom.counter0 >= 0) own_ready = meet(dom, item.layer, item.split, scr, &s_last);
+        TOC(4);
+        if (own_ready) finish(item.dom, item.layer);
+        TOC(5);
+
+        if constexpr (RIDER) {
+            if (rider_last) {
+                double *slab = p.partials + ((int64_t)gd.slab0 + (int64_t)item.layer * gd.nsplit) * (K * D);
+                __threadfence();
+                for (int i = tid; i < K * D; i += T) {
+                    double s = 0.0;
+                    for (int sp = 0; sp < gd.nsplit; ++sp) s += __ldcg(slab + (int64_t)sp * (K * D) + i);
+                    scr[i] = s;
+                }
+                __syncthreads();
+                finish(item.rider_dom, item.layer);
+            }
+        }
+        TOC(6);
     }
 }
 
@@ -646,10 +777,12 @@ __global__ void __launch_bounds__(MAXT, MINB) fp_kernel(const Params p) {
 // host: layout, planner, launch
 // ------------------------------------------------------------------------------------------
 int g_variant = 0;   // tuning hook, see dctd_fp_set_variant
+int g_fuse = 1;      // protein-level fusion of the global fingerprint (dctd_fp_set_fusion)
 
-Layout make_layout(int D, int n, int m, bool vec4) {
+Layout make_layout(int D, int n, int m, bool vec4, bool rider) {
     Layout l{};
     const int K = n - 1;
+    const int KS = rider ? 2 * K : K;
     l.vec = vec4 ? 4 : 1;
     l.G = (D + l.vec - 1) / l.vec;
     if (l.G <= kMaxThreads) {
@@ -667,12 +800,16 @@ Layout make_layout(int D, int n, int m, bool vec4) {
     const int nk = m - 1;
     const int DS = std::max(1, l.T / nk);
     l.table_len = 4 * D + 8 * m;
+    // Shared memory is kept small on purpose: what the CTAs of an SM do not take is L1, and the L1 size bounds
+    // the loads in flight.  (Tried: letting Y alias the scratch region behind the pass-2 buffers, -9 KB; the extra
+    // barrier cost more than the larger L1 gave: 5500 vs 5590 GB/s in an A/B run.)
+    const size_t f_region = ((size_t)DS * n * nk + (size_t)n * nk + (size_t)n * m) * sizeof(double);
     size_t off = 0;
     l.off_t4d = off; off += dctd::align_up((size_t)l.table_len * sizeof(float), 16);
+    l.off_cb = off;  off += dctd::align_up((size_t)kRowsPerItem * KS * sizeof(float), 16);
+    const size_t u_bytes = (size_t)(l.RL > 1 ? KS : K) * D * sizeof(double);
+    l.off_scr = off; off += dctd::align_up(std::max(u_bytes, f_region), 16);
     l.off_y = off;   off += dctd::align_up((size_t)n * D * sizeof(float), 16);
-    l.off_cb = off;  off += dctd::align_up((size_t)kRowsPerItem * K * sizeof(unsigned long long), 16);
-    const size_t scr = std::max((size_t)K * D, (size_t)DS * n * nk + (size_t)n * nk + (size_t)n * m) * sizeof(double);
-    l.off_scr = off; off += dctd::align_up(scr, 16);
     l.off_tm = off;  off += dctd::align_up((size_t)4 * m * sizeof(double), 16);
     l.off_mj = off;  off += dctd::align_up((size_t)n * K * sizeof(double), 16);
     l.smem = off;
@@ -690,6 +827,16 @@ KernelFn pick_k(int K) {
         case 5: return fp_kernel<5, VEC, U, MAXT, MINB>;
         case 6: return fp_kernel<6, VEC, U, MAXT, MINB>;
         case 7: return fp_kernel<7, VEC, U, MAXT, MINB>;
+    }
+    return nullptr;
+}
+
+template <int VEC, int MAXT, int MINB>
+KernelFn pick_rider(int K) {
+    switch (K) {
+        case 1: return fp_kernel<1, VEC, 8, MAXT, MINB, 0, 0, true>;
+        case 2: return fp_kernel<2, VEC, 8, MAXT, MINB, 0, 0, true>;
+        case 3: return fp_kernel<3, VEC, 8, MAXT, MINB, 0, 0, true>;
     }
     return nullptr;
 }
@@ -733,47 +880,148 @@ int dctd_fp_plan_create(const dctd_fp_geometry *geo, dctd_fp_plan **out_plan) {
         int32_t n_counters = 1;
         int64_t n_slabs = 0;
         pl->doms.resize((size_t)geo->n_dom);
+        pl->has_rider = false;
+
+        // rows [b, e) of protein p -> pieces (cut where the window coverage changes); l0 = domain-local index
+        auto add_pieces = [&](int p, int64_t b, int64_t e, int64_t l0) {
+            const int s0 = geo->prot_src0[p], ns = geo->prot_nsrc[p];
+            while (b < e) {
+                Piece pc{};
+                int64_t run_end;
+                if (ns == 1) {
+                    pc.src_a = s0; pc.row_a = (int32_t)b; pc.src_b = -1; pc.row_b = 0;
+                    run_end = e;
+                } else {
+                    int64_t c = std::min<int64_t>(b / stride, ns - 1);
+                    const int64_t off = b - c * stride;
+                    if (c >= 1 && off < geo->overlap) {   // covered by windows c-1 and c
+                        pc.src_a = s0 + (int32_t)c - 1; pc.row_a = (int32_t)(off + stride);
+                        pc.src_b = s0 + (int32_t)c;     pc.row_b = (int32_t)off;
+                        run_end = std::min<int64_t>(e, c * stride + geo->overlap);
+                    } else {
+                        pc.src_a = s0 + (int32_t)c; pc.row_a = (int32_t)off; pc.src_b = -1; pc.row_b = 0;
+                        run_end = (c < ns - 1) ? std::min<int64_t>(e, (c + 1) * stride) : e;
+                    }
+                }
+                pc.nrows = (int32_t)(run_end - b);
+                pc.l0 = (int32_t)l0;
+                pc.g0 = (int32_t)b;
+                pl->pieces.push_back(pc);
+                l0 += pc.nrows;
+                b = run_end;
+            }
+        };
+
+        // ---- validation + fusion analysis: a protein whose batch holds its global domain (one segment
+        //      covering every row) next to other, pairwise disjoint domains reads each row once: the other
+        //      domains' items carry the global fingerprint along ("rider"), the global domain itself only
+        //      streams the rows no other domain covers ----
+        std::vector<int64_t> dom_len((size_t)geo->n_dom, 0);
         for (int i = 0; i < geo->n_dom && rc == DCTD_OK; ++i) {
             const int p = geo->dom_prot[i];
             if (p < 0 || p >= geo->n_prot) { rc = DCTD_ERR_ARG; break; }
-            const int s0 = geo->prot_src0[p], ns = geo->prot_nsrc[p];
+            for (int j = geo->dom_seg_off[i]; j < geo->dom_seg_off[i + 1]; ++j) {
+                const int64_t b = geo->seg_beg[j], e = geo->seg_end[j];
+                if (b < 0 || e > plen[p] || e < b) { rc = DCTD_ERR_ARG; break; }
+                dom_len[i] += e - b;
+            }
+            if (rc == DCTD_OK && (dom_len[i] < geo->n || dom_len[i] > (1 << 26))) rc = DCTD_ERR_ARG;  // reference: reshape fails for L < n
+        }
+        std::vector<int32_t> global_of((size_t)geo->n_prot, -1);   // fused proteins: index of the global domain
+        std::vector<std::vector<std::pair<int64_t, int64_t>>> filler((size_t)geo->n_prot);
+        std::vector<std::vector<int32_t>> by_prot((size_t)geo->n_prot);
+        if (rc == DCTD_OK && g_fuse && geo->n <= 4) {      // rider kernels are built for n <= 4 (2n - 2 projections)
+            for (int i = 0; i < geo->n_dom; ++i) by_prot[geo->dom_prot[i]].push_back(i);
+            for (int p = 0; p < geo->n_prot; ++p) {
+                int gdom = -1;
+                for (int i : by_prot[p]) {
+                    const int j = geo->dom_seg_off[i];
+                    if (geo->dom_seg_off[i + 1] - j == 1 && geo->seg_beg[j] == 0 && geo->seg_end[j] == plen[p]) { gdom = i; break; }
+                }
+                if (gdom < 0 || by_prot[p].size() < 2) continue;
+                std::vector<std::pair<int64_t, int64_t>> segs;
+                for (int i : by_prot[p]) {
+                    if (i == gdom) continue;
+                    for (int j = geo->dom_seg_off[i]; j < geo->dom_seg_off[i + 1]; ++j)
+                        if (geo->seg_end[j] > geo->seg_beg[j]) segs.emplace_back(geo->seg_beg[j], geo->seg_end[j]);
+                }
+                std::sort(segs.begin(), segs.end());
+                bool disjoint = true;
+                for (size_t t = 1; t < segs.size(); ++t)
+                    if (segs[t].first < segs[t - 1].second) { disjoint = false; break; }
+                if (!disjoint) continue;
+                global_of[p] = gdom;
+                int64_t pos = 0;
+                for (auto &sg : segs) {
+                    if (sg.first > pos) filler[p].emplace_back(pos, sg.first);
+                    pos = sg.second;
+                }
+                if (pos < plen[p]) filler[p].emplace_back(pos, plen[p]);
+            }
+        }
+
+        // ---- pieces, domains, items ----
+        std::vector<int32_t> pivot_piece((size_t)geo->n_prot, -1);
+        std::vector<int32_t> rider_next((size_t)geo->n_dom, 0);   // next free partial-sum slot of a fused global domain
+        // first the fused global domains (their slot numbering starts with their own filler items)
+        for (int i = 0; i < geo->n_dom && rc == DCTD_OK; ++i) {
+            const int p = geo->dom_prot[i];
+            const bool fused_global = global_of[p] == i;
+            if (!fused_global) continue;
+            DomInfo di{};
+            di.piece_off = (int32_t)pl->pieces.size();
+            for (auto &rg : filler[p]) add_pieces(p, rg.first, rg.second, rg.first);
+            di.n_pieces = (int32_t)pl->pieces.size() - di.piece_off;
+            di.L = (int32_t)dom_len[i];
+            pivot_piece[p] = (int32_t)pl->pieces.size();
+            add_pieces(p, 0, 1, 0);                       // the protein's first row: pivot of all its domains
+            di.pivot = pivot_piece[p];
+            // contributors: filler items + every item of the other domains of the protein
+            int n_fill = 0;
+            for (int pi = 0; pi < di.n_pieces; ++pi)
+                n_fill += (pl->pieces[di.piece_off + pi].nrows + kRowsPerItem - 1) / kRowsPerItem;
+            int n_ride = 0;
+            for (int o : by_prot[p])
+                if (o != i) n_ride += (int)((dom_len[o] + kRowsPerItem - 1) / kRowsPerItem);
+            di.nsplit = n_fill + n_ride;
+            di.slab0 = (int32_t)n_slabs;
+            n_slabs += (int64_t)di.nsplit * geo->n_layers;
+            di.counter0 = n_counters;
+            n_counters += geo->n_layers;
+            pl->doms[i] = di;
+            rider_next[i] = n_fill;
+            pl->algo_bytes += (int64_t)geo->n_layers * geo->D * 4 * [&] { int64_t r = 0; for (auto &rg : filler[p]) r += rg.second - rg.first; return r; }();
+            for (int layer = 0; layer < geo->n_layers; ++layer) {
+                int slot = 0;
+                for (int pi = 0; pi < di.n_pieces; ++pi) {
+                    const Piece &pc = pl->pieces[di.piece_off + pi];
+                    for (int c0 = 0; c0 < pc.nrows; c0 += kRowsPerItem) {
+                        Item itm{};
+                        itm.dom = i; itm.layer = layer; itm.split = slot++;
+                        itm.r0 = pc.l0 + c0; itm.r1 = pc.l0 + std::min(pc.nrows, c0 + kRowsPerItem);
+                        itm.piece_first = pi; itm.rider_dom = -1; itm.rider_split = 0;
+                        pl->items.push_back(itm);
+                    }
+                }
+            }
+        }
+        if (n_slabs > 0x7fffffff / 2) rc = DCTD_ERR_UNSUPPORTED;
+        for (int i = 0; i < geo->n_dom && rc == DCTD_OK; ++i) {
+            const int p = geo->dom_prot[i];
+            if (global_of[p] == i) continue;
+            const int gdom = global_of[p];
             DomInfo di{};
             di.piece_off = (int32_t)pl->pieces.size();
             int64_t l0 = 0;
             for (int j = geo->dom_seg_off[i]; j < geo->dom_seg_off[i + 1]; ++j) {
-                int64_t b = geo->seg_beg[j], e = geo->seg_end[j];
-                if (b < 0 || e > plen[p] || e < b) { rc = DCTD_ERR_ARG; break; }
-                while (b < e) {
-                    Piece pc{};
-                    int64_t run_end;
-                    if (ns == 1) {
-                        pc.src_a = s0; pc.row_a = (int32_t)b; pc.src_b = -1; pc.row_b = 0;
-                        run_end = e;
-                    } else {
-                        int64_t c = std::min<int64_t>(b / stride, ns - 1);
-                        const int64_t off = b - c * stride;
-                        if (c >= 1 && off < geo->overlap) {   // covered by windows c-1 and c
-                            pc.src_a = s0 + (int32_t)c - 1; pc.row_a = (int32_t)(off + stride);
-                            pc.src_b = s0 + (int32_t)c;     pc.row_b = (int32_t)off;
-                            run_end = std::min<int64_t>(e, c * stride + geo->overlap);
-                        } else {
-                            pc.src_a = s0 + (int32_t)c; pc.row_a = (int32_t)off; pc.src_b = -1; pc.row_b = 0;
-                            run_end = (c < ns - 1) ? std::min<int64_t>(e, (c + 1) * stride) : e;
-                        }
-                    }
-                    pc.nrows = (int32_t)(run_end - b);
-                    pc.l0 = (int32_t)l0;
-                    pl->pieces.push_back(pc);
-                    l0 += pc.nrows;
-                    b = run_end;
-                }
+                add_pieces(p, geo->seg_beg[j], geo->seg_end[j], l0);
+                l0 += geo->seg_end[j] - geo->seg_beg[j];
             }
-            if (rc != DCTD_OK) break;
-            if (l0 < geo->n || l0 > (1 << 26)) { rc = DCTD_ERR_ARG; break; }  // reference: reshape fails for L < n
             di.n_pieces = (int32_t)pl->pieces.size() - di.piece_off;
             di.L = (int32_t)l0;
             di.nsplit = (int32_t)((l0 + kRowsPerItem - 1) / kRowsPerItem);
             di.slab0 = -1; di.counter0 = -1;
+            di.pivot = gdom >= 0 ? pivot_piece[p] : di.piece_off;
             if (di.nsplit > 1) {
                 di.slab0 = (int32_t)n_slabs;
                 n_slabs += (int64_t)di.nsplit * geo->n_layers;
@@ -783,6 +1031,8 @@ int dctd_fp_plan_create(const dctd_fp_geometry *geo, dctd_fp_plan **out_plan) {
             pl->doms[i] = di;
             pl->algo_bytes += (int64_t)geo->n_layers * l0 * geo->D * 4;
             const int rps = (int)((l0 + di.nsplit - 1) / di.nsplit);
+            const int ride0 = gdom >= 0 ? rider_next[gdom] : 0;
+            if (gdom >= 0) { rider_next[gdom] += di.nsplit; pl->has_rider = true; }
             for (int layer = 0; layer < geo->n_layers; ++layer) {
                 int pf = 0;
                 for (int s = 0; s < di.nsplit; ++s) {
@@ -795,6 +1045,7 @@ int dctd_fp_plan_create(const dctd_fp_geometry *geo, dctd_fp_plan **out_plan) {
                         ++pf;
                     }
                     itm.piece_first = pf;
+                    itm.rider_dom = gdom; itm.rider_split = gdom >= 0 ? ride0 + s : 0;
                     pl->items.push_back(itm);
                 }
             }
@@ -813,6 +1064,7 @@ int dctd_fp_plan_create(const dctd_fp_geometry *geo, dctd_fp_plan **out_plan) {
             pl->blob_bytes = off;
             pl->off_src = off;      off += dctd::align_up((size_t)geo->n_layers * geo->n_src * sizeof(void *), 256);
             pl->off_counters = off; off += dctd::align_up((size_t)n_counters * sizeof(int), 256);
+            pl->off_timing = off;   off += 256;
             pl->off_table = off;    off += dctd::align_up((size_t)(4 * geo->D + 8 * geo->m) * sizeof(float), 256);
             pl->off_partials = off; off += dctd::align_up((size_t)n_slabs * (geo->n - 1) * geo->D * sizeof(double), 256);
             pl->total = off;
@@ -861,7 +1113,24 @@ int32_t dctd_fp_num_items(const dctd_fp_plan *plan) { return plan ? (int32_t)pla
 /* tuning hook (not in dctd.h): selects the pass-1 unroll / occupancy variant for n == 3 */
 int dctd_fp_set_variant(int v) { g_variant = v; return DCTD_OK; }
 
-/* test hook: copies the plan's pieces (6 int32 each) / items (8 int32 each) to host buffers */
+/* DCTD_FP_TIMING builds: copies the 16 per-phase cycle counters of the last dctd_fp_execute on this
+ * workspace to the host (synchronises the device) */
+int dctd_fp_timing_read(const dctd_fp_plan *plan, const void *d_workspace, int64_t *h_out16) {
+#ifdef DCTD_FP_TIMING
+    if (!plan || !d_workspace || !h_out16) return DCTD_ERR_ARG;
+    DCTD_CUDA_TRY(cudaDeviceSynchronize());
+    DCTD_CUDA_TRY(cudaMemcpy(h_out16, (const char *)d_workspace + plan->off_timing, 128, cudaMemcpyDeviceToHost));
+    return DCTD_OK;
+#else
+    (void)plan; (void)d_workspace; (void)h_out16;
+    return DCTD_ERR_UNSUPPORTED;
+#endif
+}
+
+/* switch the protein-level fusion (global fingerprint riding on the domain items) on/off; default on */
+int dctd_fp_set_fusion(int on) { g_fuse = on ? 1 : 0; return DCTD_OK; }
+
+/* test hook: copies the plan's pieces (8 int32 each) / items (8 int32 each) to host buffers */
 int dctd_fp_plan_dump(const dctd_fp_plan *plan, int32_t *pieces, int64_t max_pieces, int32_t *items,
                       int64_t max_items, int64_t *n_pieces, int64_t *n_items) {
     if (!plan) return DCTD_ERR_ARG;
@@ -891,7 +1160,7 @@ int dctd_fp_execute(const dctd_fp_plan *plan, const void *const *h_src_ptrs, int
         if (((uintptr_t)h_src_ptrs[i] & 15) != 0) vec4 = false;
 
     Params prm{};
-    prm.lay = make_layout(plan->D, plan->n, plan->m, vec4);
+    prm.lay = make_layout(plan->D, plan->n, plan->m, vec4, plan->has_rider);
     int dev = 0, max_smem = 0, n_sm = 0;
     DCTD_CUDA_TRY(cudaGetDevice(&dev));
     DCTD_CUDA_TRY(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
@@ -905,6 +1174,9 @@ int dctd_fp_execute(const dctd_fp_plan *plan, const void *const *h_src_ptrs, int
     }
     DCTD_CUDA_TRY(cudaMemcpyAsync(ws + plan->off_src, h_src_ptrs, nptr * sizeof(void *), cudaMemcpyHostToDevice, stream));
     DCTD_CUDA_TRY(cudaMemsetAsync(ws + plan->off_counters, 0, (size_t)plan->n_counters * sizeof(int), stream));
+#ifdef DCTD_FP_TIMING
+    DCTD_CUDA_TRY(cudaMemsetAsync(ws + plan->off_timing, 0, 256, stream));
+#endif
 
     prm.src = (const float *const *)(ws + plan->off_src);
     prm.table = (const float *)(ws + plan->off_table);
@@ -913,6 +1185,7 @@ int dctd_fp_execute(const dctd_fp_plan *plan, const void *const *h_src_ptrs, int
     prm.items = (const Item *)(ws + plan->off_items);
     prm.counters = (int *)(ws + plan->off_counters);
     prm.partials = (double *)(ws + plan->off_partials);
+    prm.timing = (long long *)(ws + plan->off_timing);
     prm.out = d_out;
     prm.ld = ld;
     prm.out_stride = out_stride;
@@ -922,19 +1195,30 @@ int dctd_fp_execute(const dctd_fp_plan *plan, const void *const *h_src_ptrs, int
     prm.D = plan->D; prm.n = plan->n; prm.m = plan->m;
 
     const int K = plan->n - 1;
-    KernelFn fn;
-    if (!vec4) fn = pick_k<1, 8, kMaxThreads, 1>(K);
-    else if (prm.lay.T <= 320) {
+    KernelFn fn = nullptr;
+    const bool small = prm.lay.T <= 320;
+    const bool ldc = (ld == plan->D);
+    if (plan->has_rider) {
+        // protein-level fusion: 2K projections per element
+        if (!vec4) fn = pick_rider<1, kMaxThreads, 1>(K);
+        else if (K == 2 && ldc && plan->D == 1280 && prm.lay.RL == 1 && g_variant == 6) fn = fp_kernel<2, 4, 6, 320, 2, 1280, 1, true>;
+        else if (K == 2 && ldc && plan->D == 1280 && prm.lay.RL == 1 && g_variant == 4) fn = fp_kernel<2, 4, 4, 320, 2, 1280, 1, true>;
+        else if (K == 2 && ldc && plan->D == 1280 && prm.lay.RL == 1) fn = fp_kernel<2, 4, 8, 320, 2, 1280, 1, true>;
+        else if (K == 2 && ldc && plan->D == 640 && prm.lay.RL == 1) fn = fp_kernel<2, 4, 8, 160, 3, 640, 1, true>;
+        else if (small) fn = pick_rider<4, 320, 2>(K);
+        else fn = pick_rider<4, kMaxThreads, 1>(K);
+    } else if (!vec4) fn = pick_k<1, 8, kMaxThreads, 1>(K);
+    else if (small) {
         // tuning variants of the common case n = 3 (see DESIGN.md "pass-1 occupancy")
         if (K == 2 && g_variant == 1) fn = fp_kernel<2, 4, 4, 320, 3>;
         else if (K == 2 && g_variant == 2) fn = fp_kernel<2, 4, 8, 320, 3>;
-        else if (K == 2 && ld == plan->D && plan->D == 1280 && prm.lay.RL == 1) fn = fp_kernel<2, 4, 8, 320, 2, 1280, 1>;
-        else if (K == 2 && ld == plan->D && plan->D == 640 && prm.lay.RL == 2) fn = fp_kernel<2, 4, 8, 320, 2, 640, 2>;
-        else if (K == 2 && ld == plan->D && plan->D == 640 && prm.lay.RL == 1) fn = fp_kernel<2, 4, 8, 160, 4, 640, 1>;
-        else if (K == 2 && ld == plan->D && plan->D == 1024 && prm.lay.RL == 1) fn = fp_kernel<2, 4, 8, 256, 2, 1024, 1>;
-        else if (K == 2 && ld == plan->D && plan->D == 320 && prm.lay.RL == 4) fn = fp_kernel<2, 4, 8, 320, 2, 320, 4>;
+        else if (K == 2 && ldc && plan->D == 1280 && prm.lay.RL == 1) fn = fp_kernel<2, 4, 8, 320, 2, 1280, 1>;
+        else if (K == 2 && ldc && plan->D == 640 && prm.lay.RL == 2) fn = fp_kernel<2, 4, 8, 320, 2, 640, 2>;
+        else if (K == 2 && ldc && plan->D == 640 && prm.lay.RL == 1) fn = fp_kernel<2, 4, 8, 160, 4, 640, 1>;
+        else if (K == 2 && ldc && plan->D == 1024 && prm.lay.RL == 1) fn = fp_kernel<2, 4, 8, 256, 2, 1024, 1>;
+        else if (K == 2 && ldc && plan->D == 320 && prm.lay.RL == 4) fn = fp_kernel<2, 4, 8, 320, 2, 320, 4>;
         else fn = pick_k<4, 8, 320, 2>(K);
-    } else if (K == 2 && ld == plan->D && plan->D == 2560 && prm.lay.RL == 1) fn = fp_kernel<2, 4, 8, kMaxThreads, 1, 2560, 1>;
+    } else if (K == 2 && ldc && plan->D == 2560 && prm.lay.RL == 1) fn = fp_kernel<2, 4, 8, kMaxThreads, 1, 2560, 1>;
     else fn = pick_k<4, 8, kMaxThreads, 1>(K);
     if (!fn) return DCTD_ERR_UNSUPPORTED;
     DCTD_CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prm.lay.smem));

@@ -179,3 +179,49 @@ def test_scale_and_idct_quant_helpers_match_reference_semantics():
     q = (b.reshape(240) * 127).astype('int8')
     want = fo.quant2d_matrix(x, 3, 80)
     assert np.abs(q.astype(int) - want.astype(int)).max() <= 1
+
+
+def test_protein_level_fusion_on_and_off():
+    """A protein whose batch holds its global '1-L' domain next to disjoint domains reads each row once (the
+    domains' items carry the global fingerprint along).  Same results as the unfused plan, within tolerance."""
+    from dctdomain_b200 import _lib
+    from dctdomain_b200.fingerprint import Fingerprint, quantize_batch
+    rs = np.random.RandomState(21)
+
+    def batch():
+        fps = []
+        for i, L in enumerate([158, 409, 700, 1035, 1800]):
+            kind = synth.KINDS[i % 3]
+            if L > 500:
+                case = dict(seed=400 + i, L=L, D=640, maxlen=500, kind=kind)
+                chunks = cases.stitch_chunks_for(case)
+                emb = {lay: [c[lay] for c in chunks] for lay in (15, 21)}
+            else:
+                emb = synth.layers(400 + i, L, 640, kind)
+            doms = synth.random_partition(rs, L, 3 + i, min_len=22)
+            if i == 1:
+                doms = [doms[2] + ',' + doms[0]] + doms[1:2] + doms[3:]       # discontinuous, unsorted
+            if i == 2:
+                doms = doms[:-1]                                               # rows no domain covers
+            fps.append(Fingerprint(pid=f'f{i}', seq='A' * L, embed=emb, domains=doms + [f'1-{L}'], quants={}))
+        return fps
+
+    rs = np.random.RandomState(21)
+    fused = batch()
+    quantize_batch(fused, [3, 80, 3, 80])
+    rs = np.random.RandomState(21)
+    plain = batch()
+    _lib.lib().dctd_fp_set_fusion(0)
+    try:
+        quantize_batch(plain, [3, 80, 3, 80])
+    finally:
+        _lib.lib().dctd_fp_set_fusion(1)
+    for a, b in zip(fused, plain):
+        assert a.domains == b.domains
+        emb = {lay: (fo.stitch_chunks(v) if isinstance(v, list) else v) for lay, v in a.embed.items()}
+        want, _ = fo.quantize_matrix(emb, list(a.domains), [3, 80, 3, 80])
+        ga = np.array([a.quants[d] for d in a.domains])
+        gb = np.array([b.quants[d] for d in b.domains])
+        w = np.array([want[d] for d in a.domains])
+        _compare('fusion/on/' + a.pid, ga, w, 0.01)
+        _compare('fusion/off/' + a.pid, gb, w, 0.01)

@@ -33,10 +33,10 @@ def _plan(lib, **kw):
 def _dump(lib, plan):
     npc, nit = C.c_int64(), C.c_int64()
     lib.dctd_fp_plan_dump(plan.handle, None, 0, None, 0, C.byref(npc), C.byref(nit))
-    pieces = np.zeros((npc.value, 6), dtype=np.int32)
+    pieces = np.zeros((npc.value, 8), dtype=np.int32)
     items = np.zeros((nit.value, 8), dtype=np.int32)
     lib.dctd_fp_plan_dump(plan.handle, pieces.ctypes.data, npc.value, items.ctypes.data, nit.value, None, None)
-    return pieces, items
+    return pieces[:, :7], items
 
 
 def test_planner_single_source(lib):
@@ -44,9 +44,21 @@ def test_planner_single_source(lib):
                  dom_prot=[0, 0], dom_seg_off=[0, 2, 3], seg_beg=[176, 0, 0], seg_end=[300, 77, 300])
     pieces, items = _dump(lib, plan)
     # domain 0 = rows 176..299 then 0..76 (listed order); domain 1 = the whole protein
-    assert pieces.tolist() == [[0, 176, -1, 0, 124, 0], [0, 0, -1, 0, 77, 124], [0, 0, -1, 0, 300, 0]]
-    assert len(items) == 4 and plan.algorithmic_bytes == 2 * (201 + 300) * 1280 * 4
-    assert items[0, 3] - items[0, 2] == 300          # longest first
+    # the whole-protein domain rides on the other domain's item and only streams the rows it does not cover
+    # (77..175); the protein's first row is the common pivot piece; columns: src_a,row_a,src_b,row_b,nrows,l0,g0
+    assert pieces.tolist() == [[0, 77, -1, 0, 99, 77, 77], [0, 0, -1, 0, 1, 0, 0],
+                               [0, 176, -1, 0, 124, 0, 176], [0, 0, -1, 0, 77, 124, 0]]
+    assert len(items) == 4 and plan.algorithmic_bytes == 2 * 300 * 1280 * 4      # every row is read once
+    assert items[0, 3] - items[0, 2] == 201 and items[0, 6] == 1                 # longest first; rider = domain 1
+    lib.dctd_fp_set_fusion(0)
+    try:
+        plan2 = _plan(lib, n_layers=2, D=1280, n=3, m=80, src_rows=[300], prot_src0=[0], prot_nsrc=[1],
+                      dom_prot=[0, 0], dom_seg_off=[0, 2, 3], seg_beg=[176, 0, 0], seg_end=[300, 77, 300])
+    finally:
+        lib.dctd_fp_set_fusion(1)
+    pieces2, items2 = _dump(lib, plan2)
+    assert pieces2[:, :6].tolist() == [[0, 176, -1, 0, 124, 0], [0, 0, -1, 0, 77, 124], [0, 0, -1, 0, 300, 0]]
+    assert plan2.algorithmic_bytes == 2 * (201 + 300) * 1280 * 4 and (items2[:, 6] == -1).all()
 
 
 def test_planner_windows_and_split(lib):
@@ -58,7 +70,7 @@ def test_planner_windows_and_split(lib):
             [0, 300, 1, 0, 200, 300], [1, 200, -1, 0, 100, 500],
             [1, 300, 2, 0, 200, 600], [2, 200, -1, 0, 100, 800],
             [2, 300, 3, 0, 200, 900], [3, 200, -1, 0, 134, 1100]]
-    assert pieces.tolist() == want
+    assert pieces[:, :6].tolist() == want and (pieces[:, 6] == pieces[:, 5]).all()
     assert len(items) == 3 and sorted((int(a), int(b)) for a, b in items[:, 2:4]) == [(0, 412), (412, 824), (824, 1234)]
     assert plan.workspace_bytes >= 3 * 2 * 640 * 8
 
