@@ -33,7 +33,7 @@ def proteins_mode():
     srcs = [[layers[l][poff[p]:poff[p + 1]] for p in range(n_prot)] for l in range(2)]
     out = torch.empty((n_dom, 480), dtype=torch.int8, device='cuda')
     res = {}
-    for fuse, var in ((1, 0), (1, 6), (1, 4), (0, 0)):
+    for fuse, var in ((1, 0), (0, 0), (1, 0), (0, 0)):
         _lib.lib().dctd_fp_set_fusion(fuse)
         _lib.lib().dctd_fp_set_variant(var)
         plan = make_plan(2, D, 3, 80, plens, list(range(n_prot)), [1] * n_prot, dom_prot, list(range(n_dom + 1)), seg_beg, seg_end)
