@@ -10,6 +10,9 @@ from dctdomain_b200 import _lib
 from dctdomain_b200 import index as dindex
 
 
+MODES = [int(x) for x in os.environ.get('L1_MODES', '0,1').split(',')]
+
+
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000
     nqs = [int(x) for x in sys.argv[2].split(',')] if len(sys.argv) > 2 else [1, 8, 13, 16, 64, 256, 1024, 8192]
@@ -24,7 +27,7 @@ def main():
         q = torch.clamp(db[rows].to(torch.int16) + torch.randint(-3, 4, (nq, 480), generator=g, device=dev).to(torch.int16),
                         0, 127).to(torch.int8)
         out = {}
-        for mode in (0, 1):
+        for mode in MODES:
             _lib.lib().dctd_l1_set_mode(mode)
             for _ in range(3):
                 idx.search_device(q, 50)
@@ -37,7 +40,7 @@ def main():
             e1.record()
             torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / iters
-            out['thresh' if mode == 0 else 'heap'] = dict(ms=ms, pairs_per_s=nq * n / ms * 1e3, db_GBps=n * 480 / ms / 1e6)
+            out[{0: 'thresh', 1: 'heap'}.get(mode, f'mode{mode}')] = dict(ms=ms, pairs_per_s=nq * n / ms * 1e3, db_GBps=n * 480 / ms / 1e6)
             out['same'] = bool(out.get('same', True) and (('ref' not in out) or (torch.equal(out['ref'][0], r[0]) and torch.equal(out['ref'][1], r[1]))))
             out.setdefault('ref', r)
         out.pop('ref')
