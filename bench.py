@@ -426,8 +426,9 @@ def run_search(args, dev, rank, world, dist, torch, dindex, ShardedIndex, shard_
     sad_rate = pairs * 120 / (ms * 1e-3)
     return {'metric': 'L1 top-50 query.DB pairs/s', 'value': pairs / (ms * 1e-3), 'unit': 'pairs/s', 'ms_per_step': ms / steps,
             'steps': steps, 'scaling': 'strong', 'dtype': 'u8', 'gpu_launches': launches,
-            'config': {'workload': f'configs[3]-sized: {nq} queries x {n_db} int8[480] fingerprints, k=50, DB sharded '
-                                   f'over {world} rank(s), NCCL all-gather merge', 'n_db': n_db, 'nq': nq, 'k': k},
+            'config': {'workload': f'{"configs[4]" if n_db >= 50_000_000 else "configs[3]"}-sized: {nq} queries x {n_db} '
+                                   f'int8[480] fingerprints, k=50, DB sharded over {world} rank(s), NCCL all-gather merge',
+                       'n_db': n_db, 'nq': nq, 'k': k},
             'e2e_pairs_per_s': e2e_pairs,
             'roofline': {'bound': 'integer pipe (VABSDIFF4.U8.ACC, 120 per pair; not HBM: the database streams at '
                                   '%.1f GB/s per rank)' % (db_bytes / (ms / steps * 1e-3) / 1e9),
