@@ -30,6 +30,7 @@
 #include <vector>
 
 #include "dctd_internal.cuh"
+#include "dctd_tma.cuh"
 
 namespace {
 
@@ -72,6 +73,13 @@ struct Layout {             // thread / shared-memory layout derived from (D, n,
     size_t off_t4d, off_y, off_cb, off_scr, off_tm, off_mj;
 };
 
+struct WsLayout {           // shared-memory layout of the warp-specialised kernel (fp_ws_kernel.cuh)
+    int nst;                // TMA ring stages
+    int DS;                 // pass-2a splits of the column range
+    unsigned off_bars, off_meta, off_basis, off_desc, off_ring, off_u, off_ye, off_yo, off_f, off_tt, off_tm, off_mj;
+    unsigned smem;
+};
+
 struct Params {
     const float *const *src;
     const float *table;     // extended cosine table in the workspace (fp_table_kernel)
@@ -86,6 +94,9 @@ struct Params {
     int32_t n_src, n_items, n_layers;
     int32_t D, n, m;
     Layout lay;
+    // warp-specialised kernel only
+    const int32_t *wsitems; // fat item records (32 words each), same order as items
+    WsLayout wl;
 };
 
 }  // namespace
@@ -95,12 +106,13 @@ struct dctd_fp_plan {
     std::vector<Piece> pieces;
     std::vector<DomInfo> doms;
     std::vector<Item> items;
+    std::vector<int32_t> wsitems;   // 32 words per item (fp_ws_kernel.cuh), same order as items
     bool has_rider;           // some items carry their protein's global fingerprint along
     int32_t n_counters;       // 1 (work queue) + split arrival counters
     int64_t n_slabs;          // partial-sum slabs of (n-1)*D doubles
     int64_t algo_bytes;
     // device blob layout (bytes from the workspace base)
-    size_t off_pieces, off_doms, off_items, off_src, off_counters, off_timing, off_table, off_partials, total;
+    size_t off_pieces, off_doms, off_items, off_wsitems, off_src, off_counters, off_timing, off_table, off_partials, total;
     void *blob;               // host copy of [pieces | doms | items], pinned when possible
     bool blob_pinned;
     size_t blob_bytes;
@@ -773,11 +785,14 @@ __global__ void __launch_bounds__(MAXT, MINB) fp_kernel(const Params p) {
     }
 }
 
+#include "fp_ws_kernel.cuh"
+
 // ------------------------------------------------------------------------------------------
 // host: layout, planner, launch
 // ------------------------------------------------------------------------------------------
 int g_variant = 0;   // tuning hook, see dctd_fp_set_variant
 int g_fuse = 1;      // protein-level fusion of the global fingerprint (dctd_fp_set_fusion)
+int g_ws_stages = 0; // tuning hook: cap on the TMA ring stages of the warp-specialised kernel (0 = as many as fit)
 
 Layout make_layout(int D, int n, int m, bool vec4, bool rider) {
     Layout l{};
@@ -816,6 +831,36 @@ Layout make_layout(int D, int n, int m, bool vec4, bool rider) {
     return l;
 }
 
+// shared-memory layout of fp_ws_kernel<K, D, *>; nst = 0 if not even three stages fit
+template <int K, int DC, bool RIDER>
+WsLayout make_ws_layout(int m, int max_smem) {
+    using Cfg = WsCfg<K, DC, RIDER>;
+    WsLayout w{};
+    const int N = K + 1, nk = m - 1;
+    w.DS = std::max(1, std::min(kWsFinThreads / nk, std::max(1, DC / 8 / 8)));
+    size_t off = 0;
+    auto take = [&](size_t bytes) { const size_t o = off; off += dctd::align_up(bytes, 128); return (unsigned)o; };
+    w.off_bars = take((2 * kWsMaxStages + 4) * sizeof(unsigned long long));
+    w.off_meta = take(kWsMaxStages * sizeof(int4));
+    w.off_basis = take((size_t)kWsBasisRows * Cfg::KS * sizeof(float));
+    w.off_desc = take((size_t)kWsDescSlots * 32 * sizeof(int));
+    w.off_u = take((size_t)2 * K * DC * sizeof(double));
+    w.off_ye = take((size_t)N * (DC / 2) * sizeof(float));
+    w.off_yo = take((size_t)N * (DC / 2) * sizeof(float));
+    w.off_f = take(((size_t)w.DS * N * nk + (size_t)N * nk + (size_t)N * m) * sizeof(double));
+    w.off_tt = take((size_t)(4 * DC + 8 * m) * sizeof(float));
+    w.off_tm = take((size_t)4 * m * sizeof(double));
+    w.off_mj = take((size_t)N * K * sizeof(double));
+    w.off_ring = take(0);
+    const long long room = (long long)max_smem - (long long)off - 1024;      // 1 KB for the static shared variables
+    long long nst = room / Cfg::STAGE_BYTES;
+    if (g_ws_stages > 0) nst = std::min<long long>(nst, g_ws_stages);
+    nst = std::min<long long>(nst, kWsMaxStages);
+    w.nst = nst >= 3 ? (int)nst : 0;
+    w.smem = (unsigned)(off + (size_t)std::max(w.nst, 0) * Cfg::STAGE_BYTES);
+    return w;
+}
+
 typedef void (*KernelFn)(const Params);
 template <int VEC, int U, int MAXT, int MINB>
 KernelFn pick_k(int K) {
@@ -839,6 +884,22 @@ KernelFn pick_rider(int K) {
         case 3: return fp_kernel<3, VEC, 8, MAXT, MINB, 0, 0, true>;
     }
     return nullptr;
+}
+
+// launches fp_ws_kernel<K, DC, RIDER> if its shared-memory layout fits; *launched tells
+template <int K, int DC, bool RIDER>
+int launch_ws(const dctd_fp_plan *plan, Params &prm, int max_smem, int n_sm, cudaStream_t stream, bool *launched) {
+    using Cfg = WsCfg<K, DC, RIDER>;
+    *launched = false;
+    prm.wl = make_ws_layout<K, DC, RIDER>(plan->m, max_smem);
+    if (prm.wl.nst == 0) return DCTD_OK;
+    auto fn = fp_ws_kernel<K, DC, RIDER>;
+    DCTD_CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prm.wl.smem));
+    const int grid = std::max(1, std::min(prm.n_items, n_sm));     // one persistent CTA per SM
+    fn<<<grid, Cfg::T, prm.wl.smem, stream>>>(prm);
+    DCTD_LAUNCH_CHECK();
+    *launched = true;
+    return DCTD_OK;
 }
 
 }  // namespace
@@ -1057,10 +1118,60 @@ int dctd_fp_plan_create(const dctd_fp_geometry *geo, dctd_fp_plan **out_plan) {
             });
             pl->n_counters = n_counters;
             pl->n_slabs = n_slabs;
+            // fat item records of the warp-specialised kernel: everything its producer / finisher warps need
+            // about an item in one 128-byte read (see the word indices in fp_ws_kernel.cuh)
+            pl->wsitems.assign(pl->items.size() * 32, 0);
+            for (size_t t = 0; t < pl->items.size(); ++t) {
+                const Item &itm = pl->items[t];
+                const DomInfo &di = pl->doms[itm.dom];
+                int32_t *w = &pl->wsitems[t * 32];
+                w[kWDom] = itm.dom; w[kWLayer] = itm.layer; w[kWR0] = itm.r0; w[kWR1] = itm.r1; w[kWL] = di.L;
+                int32_t fl = 0;
+                w[kWSplit] = itm.split; w[kWNsplit] = di.nsplit;
+                w[kWSlabBase] = -1; w[kWCounter] = -1;
+                if (di.counter0 >= 0) {
+                    fl |= kWfSplit;
+                    w[kWSlabBase] = di.slab0 + itm.layer * di.nsplit;
+                    w[kWCounter] = di.counter0 + itm.layer;
+                }
+                w[kWRiderDom] = itm.rider_dom;
+                w[kWLg] = 1;
+                if (itm.rider_dom >= 0) {
+                    const DomInfo &gd = pl->doms[itm.rider_dom];
+                    fl |= kWfRider;
+                    w[kWRiderSlabBase] = gd.slab0 + itm.layer * gd.nsplit;
+                    w[kWRiderSlab] = w[kWRiderSlabBase] + itm.rider_split;
+                    w[kWRiderNsplit] = gd.nsplit;
+                    w[kWRiderCounter] = gd.counter0 + itm.layer;
+                    w[kWLg] = gd.L;
+                }
+                const Piece &pv = pl->pieces[di.pivot];
+                w[kWPivSrcA] = pv.src_a; w[kWPivRowA] = pv.row_a; w[kWPivSrcB] = pv.src_b; w[kWPivRowB] = pv.row_b;
+                int n_runs = 0;
+                for (int pi = itm.piece_first; pi < di.n_pieces; ++pi) {
+                    const Piece &pc = pl->pieces[di.piece_off + pi];
+                    if (pc.l0 >= itm.r1) break;
+                    const int a = std::max(pc.l0, itm.r0), b = std::min(pc.l0 + pc.nrows, itm.r1);
+                    if (a >= b) { rc = DCTD_ERR_ARG; break; }      // pieces of an item are contiguous by construction
+                    if (n_runs == 0) {
+                        w[kWRunSrcA] = pc.src_a; w[kWRunRowA] = pc.row_a + (a - pc.l0);
+                        w[kWRunSrcB] = pc.src_b; w[kWRunRowB] = pc.row_b + (a - pc.l0);
+                        w[kWRunRows] = b - a; w[kWRunL0] = a; w[kWRunG0] = pc.g0 + (a - pc.l0);
+                        w[kWPieceAbs] = di.piece_off + pi;
+                    }
+                    ++n_runs;
+                }
+                w[kWNRuns] = n_runs;
+                if (n_runs > 0 && w[kWRunSrcA] == pv.src_a && w[kWRunRowA] == pv.row_a && w[kWRunSrcB] == pv.src_b &&
+                    (pv.src_b < 0 || w[kWRunRowB] == pv.row_b))
+                    fl |= kWfPivotInline;
+                w[kWFlags] = fl;
+            }
             size_t off = 0;
             pl->off_pieces = off; off += dctd::align_up(pl->pieces.size() * sizeof(Piece), 256);
             pl->off_doms = off;   off += dctd::align_up(pl->doms.size() * sizeof(DomInfo), 256);
             pl->off_items = off;  off += dctd::align_up(pl->items.size() * sizeof(Item), 256);
+            pl->off_wsitems = off; off += dctd::align_up(pl->wsitems.size() * sizeof(int32_t), 256);
             pl->blob_bytes = off;
             pl->off_src = off;      off += dctd::align_up((size_t)geo->n_layers * geo->n_src * sizeof(void *), 256);
             pl->off_counters = off; off += dctd::align_up((size_t)n_counters * sizeof(int), 256);
@@ -1082,6 +1193,7 @@ int dctd_fp_plan_create(const dctd_fp_geometry *geo, dctd_fp_plan **out_plan) {
                     if (!pl->pieces.empty()) memcpy((char *)h + pl->off_pieces, pl->pieces.data(), pl->pieces.size() * sizeof(Piece));
                     if (!pl->doms.empty()) memcpy((char *)h + pl->off_doms, pl->doms.data(), pl->doms.size() * sizeof(DomInfo));
                     if (!pl->items.empty()) memcpy((char *)h + pl->off_items, pl->items.data(), pl->items.size() * sizeof(Item));
+                    if (!pl->wsitems.empty()) memcpy((char *)h + pl->off_wsitems, pl->wsitems.data(), pl->wsitems.size() * sizeof(int32_t));
                     pl->blob = h;
                 }
             }
@@ -1111,7 +1223,11 @@ int64_t dctd_fp_algorithmic_bytes(const dctd_fp_plan *plan) { return plan ? plan
 int32_t dctd_fp_num_items(const dctd_fp_plan *plan) { return plan ? (int32_t)plan->items.size() : 0; }
 
 /* tuning hook (not in dctd.h): selects the pass-1 unroll / occupancy variant for n == 3 */
-int dctd_fp_set_variant(int v) { g_variant = v; return DCTD_OK; }
+int dctd_fp_set_variant(int v) {
+    if (v >= 100) { g_ws_stages = v - 100; return DCTD_OK; }   // 100 + s: cap the TMA ring at s stages (100: no cap)
+    g_variant = v;
+    return DCTD_OK;
+}
 
 /* DCTD_FP_TIMING builds: copies the 16 per-phase cycle counters of the last dctd_fp_execute on this
  * workspace to the host (synchronises the device) */
@@ -1194,7 +1310,22 @@ int dctd_fp_execute(const dctd_fp_plan *plan, const void *const *h_src_ptrs, int
     prm.n_layers = plan->n_layers;
     prm.D = plan->D; prm.n = plan->n; prm.m = plan->m;
 
+    prm.wsitems = (const int32_t *)(ws + plan->off_wsitems);
+
     const int K = plan->n - 1;
+    // The reference's configuration (n = 3; ESM-2 t33 / t30 widths, contiguous rows) runs on the warp-specialised
+    // TMA kernel; every other shape on the general kernel below.  g_variant == 9 forces the general kernel (A/B runs).
+    if (vec4 && ld == plan->D && K == 2 && g_variant != 9 && (plan->D == 1280 || plan->D == 640)) {
+        bool launched = false;
+        int rc;
+        if (plan->D == 1280)
+            rc = plan->has_rider ? launch_ws<2, 1280, true>(plan, prm, max_smem, n_sm, stream, &launched)
+                                 : launch_ws<2, 1280, false>(plan, prm, max_smem, n_sm, stream, &launched);
+        else
+            rc = plan->has_rider ? launch_ws<2, 640, true>(plan, prm, max_smem, n_sm, stream, &launched)
+                                 : launch_ws<2, 640, false>(plan, prm, max_smem, n_sm, stream, &launched);
+        if (rc != DCTD_OK || launched) return rc;
+    }
     KernelFn fn = nullptr;
     const bool small = prm.lay.T <= 320;
     const bool ldc = (ld == plan->D);

@@ -1,0 +1,689 @@
+// Warp-specialised fingerprint kernel (included by fingerprint.cu inside its anonymous namespace).
+//
+// Same arithmetic as fp_kernel (see the header of fingerprint.cu), different machine mapping: one
+// persistent CTA per SM whose warps have fixed roles and only meet at mbarriers, so the HBM stream
+// never pauses for the per-domain epilogue:
+//
+//   warp 0            producer   pulls items from the atomic work queue (fat 128-byte item records,
+//                                fetched one item ahead), computes the per-row cosine basis and
+//                                moves the rows HBM -> shared memory with TMA bulk copies
+//                                (cp.async.bulk, SASS UBLKCP) into a ring of ~20 KB stages;
+//   warps 1..NCW      consumers  one thread per float4 column group; pivot subtraction and the
+//                                K (2K with a riding global fingerprint) projections as packed
+//                                FFMA2 from shared memory, float32 partial sums flushed into
+//                                float64 every 8 rows; at the end of an item the sums are handed
+//                                to the finishers through a double-buffered shared array;
+//   last 8 warps      finishers  everything after pass 1 (split-domain / rider bookkeeping, the
+//                                length-n inverse + column min-max, pass 2a against a cosine
+//                                table in shared memory, pass 2b, row min-max, int8 output).
+//
+// Bytes in flight are set by the ring (6 stages x 20 KB per SM at D = 1280), not by registers, and
+// the epilogue of item i overlaps the stream of items i+1, i+2.
+#pragma once
+
+constexpr int kWsFinWarps = 8;
+constexpr int kWsFinThreads = kWsFinWarps * 32;
+constexpr int kWsDescSlots = 16;     // item records in flight between producer and finishers
+constexpr int kWsMaxStages = 10;
+constexpr int kWsBasisRows = 256;    // basis ring (rows); >= 32 + stages x rows per stage + 32, power of two
+
+// stage flags
+constexpr int kStLast = 1;           // last stage of its item: hand the sums to the finishers
+constexpr int kStDual = 2;           // rows come from two windows and are averaged (embedding.py:186)
+constexpr int kStPivotOnly = 4;      // the stage holds only the item's pivot row
+constexpr int kStPivotInline = 8;    // row 0 of the stage is also the item's pivot row
+constexpr int kStExit = 16;          // no more items
+constexpr int kStRider = 32;         // the item carries its protein's global fingerprint
+
+// words of a fat item record (WsItem, 32 x int32 = 128 bytes, one word per producer lane)
+enum {
+    kWDom = 0, kWLayer, kWR0, kWR1, kWL, kWFlags, kWSplit, kWNsplit, kWSlabBase, kWCounter,
+    kWRiderDom, kWRiderSlab, kWRiderNsplit, kWRiderSlabBase, kWRiderCounter, kWLg,
+    kWPivSrcA, kWPivRowA, kWPivSrcB, kWPivRowB, kWNRuns, kWPieceAbs,
+    kWRunSrcA, kWRunRowA, kWRunSrcB, kWRunRowB, kWRunRows, kWRunL0, kWRunG0, kWSpare0, kWSpare1, kWSpare2
+};
+constexpr int kWfRider = 1, kWfPivotInline = 2, kWfSplit = 4;
+
+template <int K, int DC, bool RIDER>
+struct WsCfg {
+    static constexpr int KS = RIDER ? 2 * K : K;
+    static constexpr int NCT = DC / 4;                  // consumer threads: one per float4 column group
+    static constexpr int NCW = NCT / 32;
+    static constexpr int R = (5120 / DC) < 2 ? 2 : ((5120 / DC) > 8 ? 8 : (5120 / DC));   // rows per stage
+    static constexpr int T = 32 * (1 + NCW + kWsFinWarps);
+    static constexpr int STAGE_BYTES = R * DC * 4;
+    static constexpr int FLUSH_EVERY = (8 / R) < 1 ? 1 : (8 / R);
+    static_assert(DC % 128 == 0, "one consumer warp per 128 columns");
+    static_assert(R % 2 == 0, "dual stages hold R/2 rows of each window");
+};
+
+// per-role cycle counters (DCTD_FP_TIMING builds; scripts/fp_phases.py): one thread per role accumulates locally and
+// adds to Params::timing at exit.  Slots: 0 producer waiting for a free stage, 1 producer total, 2 consumer waiting
+// for a full stage, 3 consumer waiting for a free hand-over buffer, 4 consumer total, 5 finisher idle, 6 finisher
+// total, 7 finisher stage 1 (+ split / rider bookkeeping), 8 pass 2a, 9 output, 10 items, 11 reduce, 12 pass 2b, 13 row min-max.
+#ifdef DCTD_FP_TIMING
+#define WS_T0() long long _wt = clock64()
+#define WS_ACC(var) do { const long long _n = clock64(); (var) += _n - _wt; _wt = _n; } while (0)
+#define WS_PUT(slot, var) atomicAdd((unsigned long long *)&p.timing[slot], (unsigned long long)(var))
+#else
+#define WS_T0() do {} while (0)
+#define WS_ACC(var) do {} while (0)
+#define WS_PUT(slot, var) do {} while (0)
+#endif
+
+// wait flavour per site (0 producer / free stage, 1 consumer / full stage, 2 consumer / hand-over buffer,
+// 3 finisher / idle), selectable at build time for A/B runs: -DWS_WAIT_MODE=0 spin, 1 suspend hint, 2 sleep
+#ifndef WS_WAIT_MODE
+#define WS_WAIT_MODE 1
+#endif
+#if WS_WAIT_MODE == 0
+#define WS_WAIT(bar, par, site) mbar_wait(bar, par)
+#elif WS_WAIT_MODE == 1
+#define WS_WAIT(bar, par, site) mbar_wait_hint(bar, par, 20000u)
+#else
+#define WS_WAIT(bar, par, site) do { if ((site) == 1 || (site) == 2) mbar_wait(bar, par); else mbar_wait_sleep(bar, par, (site) == 3 ? 256u : 96u); } while (0)
+#endif
+
+__device__ __forceinline__ void lds_pk4(unsigned int addr, pk2 &lo, pk2 &hi) {
+    asm volatile("ld.shared.v2.b64 {%0,%1}, [%2];" : "=l"(lo), "=l"(hi) : "r"(addr));
+}
+
+template <int K, int DC, bool RIDER>
+__global__ void __launch_bounds__(WsCfg<K, DC, RIDER>::T, 1) fp_ws_kernel(const Params p) {
+    using Cfg = WsCfg<K, DC, RIDER>;
+    using namespace dctd::tma;
+    constexpr int N = K + 1, KS = Cfg::KS, R = Cfg::R, NCW = Cfg::NCW, NFT = kWsFinThreads;
+    constexpr int D = DC, half = DC / 2, HQ = DC / 8;
+    extern __shared__ __align__(16) unsigned char smem[];
+    const WsLayout wl = p.wl;
+    const int NST = wl.nst;
+    unsigned long long *full = reinterpret_cast<unsigned long long *>(smem + wl.off_bars);   // [NST]
+    unsigned long long *empty = full + kWsMaxStages;                                        // [NST]
+    unsigned long long *u_full = empty + kWsMaxStages;                                      // [2]
+    unsigned long long *u_empty = u_full + 2;                                               // [2]
+    int4 *metas = reinterpret_cast<int4 *>(smem + wl.off_meta);            // [NST] {nrows, flags, desc slot | basis slot << 8, rider slab}
+    float *basis = reinterpret_cast<float *>(smem + wl.off_basis);         // [kWsBasisRows][KS] ring
+    int *desc = reinterpret_cast<int *>(smem + wl.off_desc);               // [kWsDescSlots][32]
+    unsigned char *ring = smem + wl.off_ring;                              // [NST][STAGE_BYTES]
+    double *ubuf = reinterpret_cast<double *>(smem + wl.off_u);            // [2][K][D]
+    float *Ye = reinterpret_cast<float *>(smem + wl.off_ye);               // [N][D/2]  y'[d] + y'[D-1-d]
+    float *Yo = reinterpret_cast<float *>(smem + wl.off_yo);               // [N][D/2]  y'[d] - y'[D-1-d]
+    double *Fs = reinterpret_cast<double *>(smem + wl.off_f);              // Fp [DS][N][nk] | Fr [N][nk] | Z [N][m]
+    float *TT = reinterpret_cast<float *>(smem + wl.off_tt);               // cos(pi (i mod 4D) / 2D), i < 4D + 8m
+    double *Tm = reinterpret_cast<double *>(smem + wl.off_tm);             // cos(pi i / 2m), i < 4m
+    double *Mj = reinterpret_cast<double *>(smem + wl.off_mj);             // [N][K] cos(pi (2j+1) k / 2n)
+    __shared__ int u_slot[2];
+    __shared__ int s_flag, s_last, s_rlast;
+    __shared__ double s_mn[kMaxN], s_mx[kMaxN];
+    __shared__ int s_bad[kMaxN];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int m = p.m, nk = m - 1;
+
+    if (tid == 0) {
+        for (int s = 0; s < NST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], NCW); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&u_full[b], NCW); mbar_init(&u_empty[b], 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = tid; i < 4 * D + 8 * m; i += blockDim.x) TT[i] = __ldg(p.table + i);
+    for (int i = tid; i < 4 * m; i += blockDim.x) Tm[i] = cospi((double)i / (2.0 * m));
+    for (int i = tid; i < N * K; i += blockDim.x) {
+        const int j = i / K, k = i % K + 1;
+        Mj[i] = cospi((double)((2 * j + 1) * k) / (2.0 * N));
+    }
+    __syncthreads();
+
+    if (warp == 0) {
+        // =============================== producer ===============================
+        auto fetch = [&]() -> int {
+            int v = 0;
+            if (lane == 0) v = atomicAdd(&p.counters[0], 1);
+            return __shfl_sync(0xffffffffu, v, 0);
+        };
+        int s = 0;
+        unsigned int eph = 1;            // parity of the "previous" phase: a fresh barrier passes at once
+        int seq = 0;
+        int rowseq = 0;                  // data rows emitted so far: position in the basis ring
+        long long t_wait = 0, t_busy = 0;
+        (void)t_wait; (void)t_busy;
+        WS_T0();
+        // emits one stage: nr rows from pa (and pb); bslot = ring position of the basis of its first row
+        auto emit = [&](const float *pa, const float *pb, int nr, int flags, int slot, int bslot, int aux) {
+            WS_ACC(t_busy);
+            WS_WAIT(&empty[s], eph, 0);
+            WS_ACC(t_wait);
+            if (lane == 0) {
+                metas[s] = make_int4(nr, flags, slot | (bslot << 8), aux);
+                const unsigned int rb = (unsigned int)nr * D * 4u;
+                unsigned char *dst = ring + (size_t)s * Cfg::STAGE_BYTES;
+                mbar_expect_tx(&full[s], (flags & kStExit) ? 0u : (pb ? 2u * rb : rb));
+                if (!(flags & kStExit)) {
+                    bulk_g2s(dst, pa, rb, &full[s]);
+                    if (pb) bulk_g2s(dst + (R / 2) * D * 4, pb, rb, &full[s]);
+                }
+            }
+            if (++s == NST) { s = 0; eph ^= 1u; }
+        };
+        int it_cur = fetch();
+        int it_nxt = fetch();
+        int rec = (it_cur < p.n_items) ? __ldg(p.wsitems + (size_t)it_cur * 32 + lane) : 0;
+        for (;;) {
+            if (it_cur >= p.n_items) {
+                emit(nullptr, nullptr, 0, kStExit, 0, 0, 0);
+                break;
+            }
+            const int my = rec;
+            // one item ahead: the next record is in flight while this item streams
+            const int it_after = fetch();
+            int rec_n = 0;
+            if (it_nxt < p.n_items) rec_n = __ldg(p.wsitems + (size_t)it_nxt * 32 + lane);
+#define WS_W(i) __shfl_sync(0xffffffffu, my, (i))
+            const int slot = seq & (kWsDescSlots - 1);
+            desc[slot * 32 + lane] = my;
+            const int iflags = WS_W(kWFlags), layer = WS_W(kWLayer);
+            const int L = WS_W(kWL), Lg = WS_W(kWLg);
+            const int r0 = WS_W(kWR0), r1 = WS_W(kWR1);
+            const bool rider = RIDER && (iflags & kWfRider);
+            const int rider_slab = WS_W(kWRiderSlab);
+            const float *const *src = p.src + (int64_t)layer * p.n_src;
+            const int base_flags = rider ? kStRider : 0;
+            __syncwarp();       // the record in desc[] is complete before lane 0 publishes the item's first stage
+            if (!(iflags & kWfPivotInline)) {
+                const int sa = WS_W(kWPivSrcA), ra = WS_W(kWPivRowA), sb = WS_W(kWPivSrcB), rb = WS_W(kWPivRowB);
+                const float *pa = src[sa] + (int64_t)ra * D;
+                const float *pb = (sb >= 0) ? src[sb] + (int64_t)rb * D : nullptr;
+                emit(pa, pb, 1, base_flags | kStPivotOnly | (pb ? kStDual : 0), slot, 0, rider_slab);
+            }
+            const int n_runs = WS_W(kWNRuns), piece_abs = WS_W(kWPieceAbs);
+            bool first_stage = true;
+            for (int run = 0; run < n_runs; ++run) {
+                int sa, ra, sb, rb, nrows, l0, g0;
+                if (run == 0) {
+                    sa = WS_W(kWRunSrcA); ra = WS_W(kWRunRowA); sb = WS_W(kWRunSrcB); rb = WS_W(kWRunRowB);
+                    nrows = WS_W(kWRunRows); l0 = WS_W(kWRunL0); g0 = WS_W(kWRunG0);
+                } else {
+                    const Piece pc = p.pieces[piece_abs + run];       // later pieces of the item, clipped to [r0, r1)
+                    const int a = max(pc.l0, r0), b = min(pc.l0 + pc.nrows, r1);
+                    sa = pc.src_a; ra = pc.row_a + (a - pc.l0); sb = pc.src_b; rb = pc.row_b + (a - pc.l0);
+                    nrows = b - a; l0 = a; g0 = pc.g0 + (a - pc.l0);
+                }
+                const float *pa = src[sa] + (int64_t)ra * D;
+                const float *pb = (sb >= 0) ? src[sb] + (int64_t)rb * D : nullptr;
+                const int cap = pb ? R / 2 : R;
+                int have = 0;                   // rows of this run whose basis is in the ring
+                for (int done = 0; done < nrows; done += cap) {
+                    const int nr = min(cap, nrows - done);
+                    if (done + nr > have) {
+                        // basis of the next 32 rows, one row per lane: cos(pi (2l+1) k / 2L), k = 1..K, by the
+                        // Chebyshev recurrence from one cospi (float64); the ring slots written here belonged to
+                        // rows >= kWsBasisRows - 32 back, whose stages were handed back long ago
+                        const int row = have + lane;
+                        if (row < nrows) {
+                            float *bp = basis + (size_t)((rowseq + row) & (kWsBasisRows - 1)) * KS;
+#pragma unroll
+                            for (int which = 0; which < (RIDER ? 2 : 1); ++which) {
+                                if (which == 1 && !rider) {
+#pragma unroll
+                                    for (int k = 0; k < K; ++k) bp[K + k] = 0.f;
+                                    break;
+                                }
+                                const int idx = (which == 0 ? l0 : g0) + row;
+                                const int len = which == 0 ? L : Lg;
+                                const double c1 = cospi((double)(2 * idx + 1) / (2.0 * len));
+                                double ckm2 = 1.0, ckm1 = c1;
+                                bp[which * K] = (float)c1;
+#pragma unroll
+                                for (int k = 2; k <= K; ++k) {
+                                    const double ck = 2.0 * c1 * ckm1 - ckm2;
+                                    bp[which * K + k - 1] = (float)ck;
+                                    ckm2 = ckm1;
+                                    ckm1 = ck;
+                                }
+                            }
+                        }
+                        have += 32;
+                        __syncwarp();
+                    }
+                    const bool last = (run == n_runs - 1) && (done + nr == nrows);
+                    int fl = base_flags | (pb ? kStDual : 0) | (last ? kStLast : 0);
+                    if (first_stage && (iflags & kWfPivotInline)) fl |= kStPivotInline;
+                    first_stage = false;
+                    emit(pa + (int64_t)done * D, pb ? pb + (int64_t)done * D : nullptr, nr, fl, slot,
+                         (rowseq + done) & (kWsBasisRows - 1), rider_slab);
+                }
+                rowseq += nrows;
+            }
+#undef WS_W
+            ++seq;
+            it_cur = it_nxt;
+            it_nxt = it_after;
+            rec = rec_n;
+        }
+        WS_ACC(t_busy);
+        if (lane == 0) { WS_PUT(0, t_wait); WS_PUT(1, t_wait + t_busy); WS_PUT(10, seq); }
+    } else if (warp <= NCW) {
+        // =============================== consumers ===============================
+        const int ctid = tid - 32;
+        const int col = ctid * 4;
+        const unsigned int ring_u32 = smem_u32(ring) + (unsigned int)ctid * 16u;
+        int s = 0, ub = 0, nflush = 0;
+        unsigned int fph = 0, uph = 1;
+        double acc[KS][4];
+        pk2 a0[KS], a1[KS];
+        const pk2 zero = pk(0.f, 0.f), hf = pk(0.5f, 0.5f), neg = pk(-1.f, -1.f);
+#pragma unroll
+        for (int k = 0; k < KS; ++k) {
+            a0[k] = zero; a1[k] = zero;
+#pragma unroll
+            for (int v = 0; v < 4; ++v) acc[k][v] = 0.0;
+        }
+        pk2 npiv0 = zero, npiv1 = zero;
+        long long t_full = 0, t_u = 0, t_busy = 0;
+        (void)t_full; (void)t_u; (void)t_busy;
+        WS_T0();
+        for (;;) {
+            WS_ACC(t_busy);
+            WS_WAIT(&full[s], fph, 1);
+            WS_ACC(t_full);
+            const int4 mt = metas[s];
+            const int nrows = mt.x, flags = mt.y;
+            if (flags & kStExit) {
+                WS_WAIT(&u_empty[ub], uph, 2);
+                if (ctid == 0) u_slot[ub] = -1;
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&u_full[ub]);
+                break;
+            }
+            const unsigned int st = ring_u32 + (unsigned int)s * Cfg::STAGE_BYTES;
+            const int bslot = mt.z >> 8;
+            if (nrows == R && !(flags & (kStDual | kStPivotOnly))) {
+                // the common stage: R rows of one source.  Straight-line code: every load is issued before the
+                // first use, and the stage goes back to the producer as soon as the loads have been performed
+                // (the basis ring is not part of the stage: its slots are recycled 256 rows later, see the producer)
+                // Without a rider all basis values are fetched up front as well (measured: +2 % at D = 1280, +6 % at
+                // D = 640); with a rider (twice the projections) that would spill, so they are fetched row by row.
+                constexpr int CR = RIDER ? 1 : R;
+                pk2 x0[R], x1[R], c[CR][KS];
+#pragma unroll
+                for (int r = 0; r < R; ++r) lds_pk4(st + r * D * 4, x0[r], x1[r]);
+                if constexpr (!RIDER) {
+#pragma unroll
+                    for (int r = 0; r < R; ++r)
+                        load_basis<KS>(basis + (size_t)((bslot + r) & (kWsBasisRows - 1)) * KS, c[r]);
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[s]);
+                if (flags & kStPivotInline) {
+                    npiv0 = mul2(x0[0], neg);
+                    npiv1 = mul2(x1[0], neg);
+                }
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    if constexpr (RIDER) load_basis<KS>(basis + (size_t)((bslot + r) & (kWsBasisRows - 1)) * KS, c[0]);
+                    const pk2 t0 = add2(x0[r], npiv0), t1 = add2(x1[r], npiv1);
+#pragma unroll
+                    for (int k = 0; k < KS; ++k) {
+                        a0[k] = fma2(t0, c[RIDER ? 0 : r][k], a0[k]);
+                        a1[k] = fma2(t1, c[RIDER ? 0 : r][k], a1[k]);
+                    }
+                }
+            } else {
+                // partial stages, rows averaged from two windows, pivot-only stages
+                pk2 x0[R], x1[R];
+#pragma unroll
+                for (int r = 0; r < R; ++r) { x0[r] = zero; x1[r] = zero; }
+                if (!(flags & kStDual)) {
+#pragma unroll
+                    for (int r = 0; r < R; ++r)
+                        if (r < nrows) lds_pk4(st + r * D * 4, x0[r], x1[r]);
+                } else {
+#pragma unroll
+                    for (int r = 0; r < R / 2; ++r) {
+                        if (r < nrows) {
+                            pk2 y0, y1;
+                            lds_pk4(st + r * D * 4, x0[r], x1[r]);
+                            lds_pk4(st + (R / 2 + r) * D * 4, y0, y1);
+                            x0[r] = mul2(add2(x0[r], y0), hf);      // embedding.py:186: (prev + cur) / 2 in float32
+                            x1[r] = mul2(add2(x1[r], y1), hf);
+                        }
+                    }
+                }
+                if (flags & (kStPivotOnly | kStPivotInline)) {
+                    npiv0 = mul2(x0[0], neg);
+                    npiv1 = mul2(x1[0], neg);
+                }
+                if (!(flags & kStPivotOnly)) {
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        if (r < nrows) {
+                            const pk2 t0 = add2(x0[r], npiv0), t1 = add2(x1[r], npiv1);
+                            pk2 c[KS];
+                            load_basis<KS>(basis + (size_t)((bslot + r) & (kWsBasisRows - 1)) * KS, c);
+#pragma unroll
+                            for (int k = 0; k < KS; ++k) {
+                                a0[k] = fma2(t0, c[k], a0[k]);
+                                a1[k] = fma2(t1, c[k], a1[k]);
+                            }
+                        }
+                    }
+                }
+                // the stage's rows and basis are consumed: give it back to the producer
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[s]);
+            }
+            if (++s == NST) { s = 0; fph ^= 1u; }
+            if (flags & kStPivotOnly) continue;
+            if (++nflush == Cfg::FLUSH_EVERY || (flags & kStLast)) {
+                nflush = 0;
+#pragma unroll
+                for (int k = 0; k < KS; ++k) {
+                    float f0, f1, f2, f3;
+                    unpk(a0[k], f0, f1);
+                    unpk(a1[k], f2, f3);
+                    acc[k][0] += (double)f0; acc[k][1] += (double)f1;
+                    acc[k][2] += (double)f2; acc[k][3] += (double)f3;
+                    a0[k] = zero; a1[k] = zero;
+                }
+            }
+            if (flags & kStLast) {
+                // hand the item's sums to the finishers
+                WS_ACC(t_busy);
+                WS_WAIT(&u_empty[ub], uph, 2);
+                WS_ACC(t_u);
+                double *u = ubuf + (size_t)ub * K * D;
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    *reinterpret_cast<double2 *>(u + k * D + col) = make_double2(acc[k][0], acc[k][1]);
+                    *reinterpret_cast<double2 *>(u + k * D + col + 2) = make_double2(acc[k][2], acc[k][3]);
+                }
+                if constexpr (RIDER) {
+                    if (flags & kStRider) {     // the rider's partial sums go straight to its workspace slab
+                        double *slab = p.partials + (int64_t)mt.w * (K * D);
+#pragma unroll
+                        for (int k = 0; k < K; ++k) {
+                            *reinterpret_cast<double2 *>(slab + k * D + col) = make_double2(acc[K + k][0], acc[K + k][1]);
+                            *reinterpret_cast<double2 *>(slab + k * D + col + 2) = make_double2(acc[K + k][2], acc[K + k][3]);
+                        }
+                        __threadfence();
+                    }
+                }
+                if (ctid == 0) u_slot[ub] = mt.z & 255;
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&u_full[ub]);
+                if (++ub == 2) { ub = 0; uph ^= 1u; }
+#pragma unroll
+                for (int k = 0; k < KS; ++k)
+#pragma unroll
+                    for (int v = 0; v < 4; ++v) acc[k][v] = 0.0;
+            }
+        }
+        WS_ACC(t_busy);
+        if (ctid == 0) { WS_PUT(2, t_full); WS_PUT(3, t_u); WS_PUT(4, t_full + t_u + t_busy); }
+    } else {
+        // =============================== finishers ===============================
+        const int ftid = tid - 32 * (1 + NCW);
+        const int fwarp = ftid >> 5;
+        const int DS = wl.DS;
+        double *Fp = Fs;                                   // [DS][N][nk]
+        double *Fr = Fs + (size_t)DS * N * nk;             // [N][nk]
+        double *Z = Fr + (size_t)N * nk;                   // [N][m]
+        auto fin_bar = [&]() { named_bar_sync(1, NFT); };
+
+        // length-n inverse + per-column min-max of one column (fingerprint.py:138-140), y' - 0.5 as float
+        auto column = [&](const double (&u)[K], float (&yo)[N]) {
+            double y[N];
+            double mn = INFINITY, mx = -INFINITY;
+            bool bad = false;
+#pragma unroll
+            for (int j = 0; j < N; ++j) {
+                double sacc = 0.0;
+#pragma unroll
+                for (int k = 0; k < K; ++k) sacc = fma(Mj[j * K + k], u[k], sacc);
+                y[j] = sacc;
+                bad = bad || !(sacc == sacc);
+                mn = fmin(mn, sacc);
+                mx = fmax(mx, sacc);
+            }
+            bad = bad || !(mx > mn);
+            if (bad) s_flag = 1;       // constant / non-finite column: the reference yields NaN -> all 0
+            const double inv = 1.0 / (mx - mn);
+#pragma unroll
+            for (int j = 0; j < N; ++j) yo[j] = (float)((y[j] - mn) * inv - 0.5);
+        };
+        // Ye / Yo from the u sums; cos(pi (2(D-1-d)+1) k / 2D) = (-1)^k cos(pi (2d+1) k / 2D), so even k only
+        // need e[d] = y'[d] + y'[D-1-d] and odd k only o[d] = y'[d] - y'[D-1-d], d < D/2
+        auto stage1 = [&](auto getu) {
+            for (int d = ftid; d < half; d += NFT) {
+                double ua[K], ub2[K];
+#pragma unroll
+                for (int k = 0; k < K; ++k) { ua[k] = getu(k, d); ub2[k] = getu(k, D - 1 - d); }
+                float ya[N], yb[N];
+                column(ua, ya);
+                column(ub2, yb);
+#pragma unroll
+                for (int j = 0; j < N; ++j) {
+                    Ye[j * half + d] = ya[j] + yb[j];
+                    Yo[j * half + d] = ya[j] - yb[j];
+                }
+            }
+        };
+        // passes 2a / 2b, row min-max and the int8 output of one (domain, layer) whose Ye / Yo are ready
+        long long t_idle = 0, t_s1 = 0, t_2a = 0, t_rest = 0, t_red = 0, t_2b = 0, t_mm = 0;
+        (void)t_idle; (void)t_s1; (void)t_2a; (void)t_rest; (void)t_red; (void)t_2b; (void)t_mm;
+        WS_T0();
+        auto finish_rest = [&](int dom_index, int layer) {
+            WS_ACC(t_s1);
+            // ---- pass 2a: F[j][k] = sum_{d < D/2} (e|o)[j][d] cos(pi (2d+1) k / 2D).  Cosines from the shared table
+            //      TT[i] = cos(pi (i mod 4D) / 2D) at i = (2d+1) k (lanes hold consecutive k, the stride 2d+1 is odd:
+            //      conflict-free), four columns per step at i + {0, 2k, 4k, 6k} (the table is extended by 8m entries, so
+            //      only i itself wraps); e / o are broadcast 16-byte loads ----
+            for (int w = ftid; w < nk * DS; w += NFT) {
+                const int k = 1 + w % nk, ds = w / nk;
+                // split boundaries in multiples of 8 quads (32 columns) when the width allows: no remainder loop
+                const int q0 = (HQ % 8 == 0) ? (HQ / 8 * ds / DS) * 8 : HQ * ds / DS;
+                const int q1 = (HQ % 8 == 0) ? (HQ / 8 * (ds + 1) / DS) * 8 : HQ * (ds + 1) / DS;
+                const float *yb = ((k & 1) ? Yo : Ye) + 4 * q0;
+                int idx = (int)(((long long)(8 * q0 + 1) * k) % (4LL * D));
+                const int s1 = 2 * k, s2 = 4 * k, s3 = 6 * k, s4 = 8 * k;
+                double f64[N];
+#pragma unroll
+                for (int j = 0; j < N; ++j) f64[j] = 0.0;
+                const pk2 zero = pk(0.f, 0.f);
+                pk2 a[N][2];
+#pragma unroll
+                for (int j = 0; j < N; ++j) { a[j][0] = zero; a[j][1] = zero; }
+                auto quad = [&]() {
+                    const pk2 c01 = pk(TT[idx], TT[idx + s1]), c23 = pk(TT[idx + s2], TT[idx + s3]);
+                    idx += s4;
+                    if (idx >= 4 * D) idx -= 4 * D;
+#pragma unroll
+                    for (int j = 0; j < N; ++j) {
+                        const float4 v = *reinterpret_cast<const float4 *>(yb + j * half);
+                        a[j][0] = fma2(pk(v.x, v.y), c01, a[j][0]);
+                        a[j][1] = fma2(pk(v.z, v.w), c23, a[j][1]);
+                    }
+                    yb += 4;
+                };
+                auto flush = [&]() {
+#pragma unroll
+                    for (int j = 0; j < N; ++j) {
+                        float l0, h0, l1, h1;
+                        unpk(a[j][0], l0, h0);
+                        unpk(a[j][1], l1, h1);
+                        f64[j] += (double)((l0 + h0) + (l1 + h1));
+                        a[j][0] = zero; a[j][1] = zero;
+                    }
+                };
+                int q = q0;
+                for (; q + 8 <= q1; q += 8) {             // 32 columns in float32 (4 chains of 8), then float64
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) quad();
+                    flush();
+                }
+                if (q < q1) {
+                    for (; q < q1; ++q) quad();
+                    flush();
+                }
+#pragma unroll
+                for (int j = 0; j < N; ++j) Fp[((size_t)ds * N + j) * nk + (k - 1)] = f64[j];
+            }
+            fin_bar();
+            WS_ACC(t_2a);
+            for (int i = ftid; i < N * nk; i += NFT) {
+                double f = 0.0;
+                for (int ds = 0; ds < DS; ++ds) f += Fp[(size_t)ds * N * nk + i];
+                Fr[i] = f;
+            }
+            fin_bar();
+            WS_ACC(t_red);
+            // ---- pass 2b: Z[j][c] = sum_k cos(pi (2c+1) k / 2m) F[j][k], four interleaved float64 chains.  Lanes hold
+            //      consecutive c; walking k in lockstep would make the table stride 2(k+1) doubles between lanes (a 16- or
+            //      32-way bank conflict whenever k+1 is a multiple of 4 or 8), so every lane starts at its own k ----
+            for (int w = ftid; w < N * m; w += NFT) {
+                const int j = w / m, c = w % m;
+                const int stepc = 2 * c + 1;
+                const double *fr = Fr + j * nk;
+                int kk = lane % nk;
+                int idx = (int)(((long long)stepc * (kk + 1)) % (4 * m));
+                double z[4] = {0.0, 0.0, 0.0, 0.0};
+                auto term = [&](double &zz) {
+                    zz = fma(Tm[idx], fr[kk], zz);
+                    idx += stepc;
+                    if (idx >= 4 * m) idx -= 4 * m;
+                    if (++kk == nk) { kk = 0; idx = stepc; }
+                };
+                int it = 0;
+                for (; it + 4 <= nk; it += 4) { term(z[0]); term(z[1]); term(z[2]); term(z[3]); }
+                for (; it < nk; ++it) term(z[0]);
+                Z[w] = (z[0] + z[1]) + (z[2] + z[3]);
+            }
+            fin_bar();
+            WS_ACC(t_2b);
+            // ---- per-row min-max (one warp per row), *127, truncating int8 cast (fingerprint.py:193-195) ----
+            for (int j = fwarp; j < N; j += kWsFinWarps) {
+                double mn = INFINITY, mx = -INFINITY;
+                int bad = 0;
+                for (int c = lane; c < m; c += 32) {
+                    const double z = Z[j * m + c];
+                    bad |= !(z == z);
+                    mn = fmin(mn, z);
+                    mx = fmax(mx, z);
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+                    mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+                    bad |= __shfl_xor_sync(0xffffffffu, bad, o);
+                }
+                if (lane == 0) { s_mn[j] = mn; s_mx[j] = mx; s_bad[j] = bad || !(mx > mn); }
+            }
+            fin_bar();
+            WS_ACC(t_mm);
+            const bool layer_bad = s_flag != 0;
+            int8_t *out = p.out + (int64_t)dom_index * p.out_stride + (int64_t)layer * (N * m);
+            for (int w = ftid; w < N * m; w += NFT) {
+                const int j = w / m;
+                int qv = 0;
+                if (!layer_bad && !s_bad[j]) qv = (int)(((Z[w] - s_mn[j]) / (s_mx[j] - s_mn[j])) * 127.0);
+                out[w] = (int8_t)qv;
+            }
+            fin_bar();      // s_flag / Z / s_mn are reused by the next finish
+            WS_ACC(t_rest);
+        };
+
+        // dst[i] = sum over the nsl partial-sum slabs, added in slot order (so the result does not depend on which
+        // CTA arrives last); the loads of one slab row are independent, EPT of them in flight per thread
+        auto sum_slabs = [&](double *dst, const double *slab, int nsl) {
+            constexpr int EPT = (K * D + NFT - 1) / NFT;
+            double sacc[EPT];
+#pragma unroll
+            for (int e = 0; e < EPT; ++e) sacc[e] = 0.0;
+            for (int sp = 0; sp < nsl; ++sp) {
+                const double *row = slab + (int64_t)sp * (K * D);
+                double v[EPT];
+#pragma unroll
+                for (int e = 0; e < EPT; ++e) {
+                    const int i = ftid + e * NFT;
+                    v[e] = (i < K * D) ? __ldcg(row + i) : 0.0;
+                }
+#pragma unroll
+                for (int e = 0; e < EPT; ++e) sacc[e] += v[e];
+            }
+#pragma unroll
+            for (int e = 0; e < EPT; ++e) {
+                const int i = ftid + e * NFT;
+                if (i < K * D) dst[i] = sacc[e];
+            }
+        };
+
+        int fb = 0;
+        unsigned int fph = 0;
+        for (;;) {
+            WS_ACC(t_s1);
+            WS_WAIT(&u_full[fb], fph, 3);
+            WS_ACC(t_idle);
+            const int slot = u_slot[fb];
+            if (slot < 0) break;
+            const int *ds_ = desc + slot * 32;
+            const int dom = ds_[kWDom], layer = ds_[kWLayer], iflags = ds_[kWFlags];
+            double *u = ubuf + (size_t)fb * K * D;
+            if (ftid == 0) {
+                s_flag = 0;
+                s_rlast = 0;
+                if (RIDER && (iflags & kWfRider)) {
+                    // the consumers wrote this item's rider sums to the slab (and fenced) before the hand-over
+                    const int ticket = atomicAdd(&p.counters[ds_[kWRiderCounter]], 1);
+                    s_rlast = (ticket == ds_[kWRiderNsplit] - 1);
+                }
+            }
+            bool own_ready = true;
+            if (iflags & kWfSplit) {
+                // a domain assembled from several items: publish this item's sums, the last to arrive adds them up
+                const int nsplit = ds_[kWNsplit];
+                double *slab = p.partials + (int64_t)ds_[kWSlabBase] * (K * D);
+                double *mine = slab + (int64_t)ds_[kWSplit] * (K * D);
+                for (int i = ftid; i < K * D; i += NFT) mine[i] = u[i];
+                __threadfence();
+                fin_bar();
+                if (ftid == 0) {
+                    const int ticket = atomicAdd(&p.counters[ds_[kWCounter]], 1);
+                    s_last = (ticket == nsplit - 1);
+                }
+                fin_bar();
+                own_ready = s_last != 0;
+                if (own_ready) {
+                    __threadfence();
+                    sum_slabs(u, slab, nsplit);     // the hand-over buffer is ours until it is released below
+                    fin_bar();
+                }
+            } else {
+                fin_bar();
+            }
+            const bool rider_last = RIDER && (s_rlast != 0);
+            auto from_u = [&](int k, int d) { return u[k * D + d]; };
+            if (own_ready) stage1(from_u);
+            fin_bar();
+            if constexpr (RIDER) {
+                if (rider_last) {
+                    // last contributor of the protein's global fingerprint: finish this item's own domain, then add
+                    // the rider slabs in slot order into the (still owned) hand-over buffer and finish the global one
+                    if (own_ready) finish_rest(dom, layer);
+                    if (ftid == 0) s_flag = 0;
+                    __threadfence();
+                    sum_slabs(u, p.partials + (int64_t)ds_[kWRiderSlabBase] * (K * D), ds_[kWRiderNsplit]);
+                    fin_bar();
+                    stage1(from_u);
+                    fin_bar();
+                }
+            }
+            if (ftid == 0) mbar_arrive(&u_empty[fb]);      // every finisher thread is done with ubuf[fb]
+            if (++fb == 2) { fb = 0; fph ^= 1u; }
+            if (rider_last) finish_rest(ds_[kWRiderDom], layer);
+            else if (own_ready) finish_rest(dom, layer);
+            else fin_bar();                                 // s_last / s_rlast are rewritten by the next iteration
+        }
+        WS_ACC(t_s1);
+        if (ftid == 0) { WS_PUT(5, t_idle); WS_PUT(6, t_idle + t_s1 + t_2a + t_rest + t_red + t_2b + t_mm); WS_PUT(7, t_s1); WS_PUT(8, t_2a); WS_PUT(9, t_rest);
+                          WS_PUT(11, t_red); WS_PUT(12, t_2b); WS_PUT(13, t_mm); }
+    }
+}

@@ -27,8 +27,11 @@
 #include <algorithm>
 
 #include "dctd_internal.cuh"
+#include "dctd_tma.cuh"
 
 namespace {
+
+using namespace dctd::tma;
 
 constexpr int kWarps = 8;            // warps per CTA of the scan kernel
 constexpr int kTDmax = 2;            // database groups (of 32 vectors) per shared-memory stage (1 for wide d)
@@ -116,58 +119,6 @@ __device__ __forceinline__ int warp_refine(unsigned long long *buf, int cnt, int
     return keep;
 }
 
-// ------------------------------------------------------------------------------------------
-// mbarrier / TMA bulk copy (cp.async.bulk: SASS UBLKCP)
-// ------------------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned int smem_u32(const void *p) {
-    return (unsigned int)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned int bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned int parity) {
-    unsigned int done = 0;
-    while (!done) {
-        asm volatile(
-            "{\n"
-            ".reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-            "selp.u32 %0, 1, 0, p;\n"
-            "}\n"
-            : "=r"(done)
-            : "r"(smem_u32(bar)), "r"(parity)
-            : "memory");
-    }
-}
-// producer-side wait: sleeps between probes so that the spinning lane does not take issue slots from
-// the compute warps of its scheduler
-__device__ __forceinline__ void mbar_wait_backoff(unsigned long long *bar, unsigned int parity) {
-    unsigned int done = 0;
-    for (;;) {
-        asm volatile(
-            "{\n"
-            ".reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-            "selp.u32 %0, 1, 0, p;\n"
-            "}\n"
-            : "=r"(done)
-            : "r"(smem_u32(bar)), "r"(parity)
-            : "memory");
-        if (done) break;
-        __nanosleep(400);
-    }
-}
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned int bytes, unsigned long long *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-
 // acc + sum_i |a.byte[i] - b.byte[i]| (unsigned bytes): SASS VABSDIFF4.U8.ACC
 __device__ __forceinline__ unsigned int sad4(unsigned int a, unsigned int b, unsigned int acc) {
     unsigned int r;
@@ -175,9 +126,6 @@ __device__ __forceinline__ unsigned int sad4(unsigned int a, unsigned int b, uns
     return r;
 }
 
-__device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
 
 // bitonic merge of a bitonic sequence of `cap` keys (first half ascending, second half descending)
 __device__ __forceinline__ void warp_bitonic_merge(unsigned long long *buf, int cap, int lane) {

@@ -1,0 +1,102 @@
+"""A/B run (GPU box): general fingerprint kernel (variant 9) against the warp-specialised TMA kernel (variant 0),
+alternating inside one process, on three workloads: configs[1]-shaped independent domains at D = 1280 and 640, and a
+protein-shaped batch (4 domains + the riding global fingerprint).  Reports GB/s of algorithmic bytes and how many
+output bytes differ between the two kernels.
+
+    python scripts/fp_ab.py [n_dom] [ring-stage caps, e.g. 0,5,3]
+"""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from dctdomain_b200 import _lib
+from dctdomain_b200.fingerprint import execute_plan, make_plan
+
+L = _lib.lib()
+
+
+def timed(plan, srcs, out, iters=10):
+    for _ in range(3):
+        execute_plan(plan, srcs, out)
+    torch.cuda.synchronize()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    ev[0].record()
+    for _ in range(iters):
+        execute_plan(plan, srcs, out, tables_resident=True)
+    ev[1].record()
+    torch.cuda.synchronize()
+    return ev[0].elapsed_time(ev[1]) / iters
+
+
+def ab(name, plan, srcs, out, unique_bytes, variants, res):
+    ref = None
+    for label, var, stages in variants:
+        L.dctd_fp_set_variant(var)
+        L.dctd_fp_set_variant(100 + stages)
+        ms = timed(plan, srcs, out)
+        o = out.cpu().numpy().copy()
+        if ref is None:
+            ref = o
+        diff = int((o != ref).sum())
+        maxd = int(np.abs(o.astype(int) - ref.astype(int)).max())
+        r = dict(ms=round(ms, 4), GBps=round(unique_bytes / ms / 1e6, 1), fp_per_s=round(out.shape[0] / ms * 1e3),
+                 bytes_differing_from_first=diff, max_abs_diff=maxd)
+        res.setdefault(name, {}).setdefault(label, []).append(r)
+        print(name, label, r, flush=True)
+    L.dctd_fp_set_variant(0)
+    L.dctd_fp_set_variant(100)
+
+
+def domains(n_dom, D, variants, res, lo=40, hi=500):
+    rs = np.random.RandomState(0)
+    lens = rs.randint(lo, hi + 1, size=n_dom)
+    off = np.concatenate([[0], np.cumsum(lens)])
+    total = int(off[-1])
+    torch.manual_seed(0)
+    layers = [torch.randn(total, D, device='cuda') for _ in range(2)]
+    plan = make_plan(2, D, 3, 80, [total], [0], [1], [0] * n_dom, list(range(n_dom + 1)), off[:-1], off[1:])
+    out = torch.empty((n_dom, 480), dtype=torch.int8, device='cuda')
+    ab(f'domains_{n_dom}x{D}_L{lo}-{hi}', plan, [[layers[0]], [layers[1]]], out, plan.algorithmic_bytes, variants, res)
+
+
+def proteins(n_prot, D, variants, res):
+    rs = np.random.RandomState(0)
+    plens = rs.randint(200, 1001, size=n_prot)
+    poff = np.concatenate([[0], np.cumsum(plens)])
+    total = int(poff[-1])
+    torch.manual_seed(0)
+    layers = [torch.randn(total, D, device='cuda') for _ in range(2)]
+    dom_prot, sb, se = [], [], []
+    for p, Lp in enumerate(plens):
+        cuts = np.sort(rs.choice(np.arange(30, Lp - 30, 25), size=3, replace=False))
+        edges = [0] + [int(c) for c in cuts] + [int(Lp)]
+        for a, b in zip(edges[:-1], edges[1:]):
+            dom_prot.append(p); sb.append(a); se.append(b)
+        dom_prot.append(p); sb.append(0); se.append(int(Lp))
+    nd = len(dom_prot)
+    srcs = [[layers[l][poff[p]:poff[p + 1]] for p in range(n_prot)] for l in range(2)]
+    plan = make_plan(2, D, 3, 80, plens, list(range(n_prot)), [1] * n_prot, dom_prot, list(range(nd + 1)), sb, se)
+    out = torch.empty((nd, 480), dtype=torch.int8, device='cuda')
+    ab(f'proteins_{n_prot}x{D}_fused', plan, srcs, out, 2 * total * D * 4, variants, res)
+
+
+def main():
+    n_dom = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+    caps = [int(v) for v in sys.argv[2].split(',')] if len(sys.argv) > 2 else [0]
+    variants = [('general', 9, 0)] + [(f'ws_stages{c or "max"}', 0, c) for c in caps]
+    variants = variants + variants
+    res = {}
+    domains(n_dom, 1280, variants, res)
+    proteins(n_dom // 2, 1280, variants, res)
+    domains(n_dom, 640, variants, res)
+    domains(n_dom * 2, 1280, variants, res, lo=40, hi=120)
+    os.makedirs('gpurun_out', exist_ok=True)
+    json.dump(res, open('gpurun_out/fp_ab.json', 'w'), indent=1)
+
+
+if __name__ == '__main__':
+    main()

@@ -13,20 +13,38 @@ from dctdomain_b200.fingerprint import execute_plan, make_plan
 
 NAMES = ['fetch', 'basis', 'stream', 'rider_handoff', 'meet', 'finish_total', 'rider_finish', '-', 'fin_minmax1', 'fin_fold',
          'fin_pass2a', 'fin_reduce', 'fin_pass2b', 'fin_minmax2', 'fin_out', '-']
+# warp-specialised kernel (fp_ws_kernel.cuh): one sampled thread per role, cycles summed over the CTAs
+WS_NAMES = ['prod_wait_free_stage', 'prod_total', 'cons_wait_full_stage', 'cons_wait_handover', 'cons_total', 'fin_idle',
+            'fin_total', 'fin_stage1', 'fin_pass2a', 'fin_out', 'items', 'fin_reduce', 'fin_pass2b', 'fin_minmax2']
 
 
 def run(name, plan, srcs, out):
-    ws = torch.empty(plan.workspace_bytes, dtype=torch.uint8, device='cuda')
-    for _ in range(3):
-        execute_plan(plan, srcs, out, workspace=ws)
-    torch.cuda.synchronize()
-    buf = np.zeros(16, dtype=np.int64)
-    _lib.check(_lib.lib().dctd_fp_timing_read(plan.handle, ws.data_ptr(), buf.ctypes.data))
-    tot = buf[[0, 1, 2, 3, 4, 5, 6]].sum()
-    rep = {n: round(float(v) / tot, 4) for n, v in zip(NAMES, buf) if n != '-'}
-    rep['cycles_per_item'] = float(tot) / plan.n_items
-    print(name, json.dumps(rep), flush=True)
-    return rep
+    res = {}
+    for label, variant in (('general', 9), ('ws', 0)):
+        _lib.lib().dctd_fp_set_variant(variant)
+        ws = torch.empty(plan.workspace_bytes, dtype=torch.uint8, device='cuda')
+        for _ in range(3):
+            execute_plan(plan, srcs, out, workspace=ws)
+        torch.cuda.synchronize()
+        buf = np.zeros(16, dtype=np.int64)
+        _lib.check(_lib.lib().dctd_fp_timing_read(plan.handle, ws.data_ptr(), buf.ctypes.data))
+        if variant == 9:
+            tot = buf[[0, 1, 2, 3, 4, 5, 6]].sum()
+            rep = {n: round(float(v) / tot, 4) for n, v in zip(NAMES, buf) if n != '-'}
+            rep['cycles_per_item'] = float(tot) / plan.n_items
+        else:
+            rep = {n: int(v) for n, v in zip(WS_NAMES, buf)}
+            rep['prod_wait_frac'] = round(buf[0] / max(1, buf[1]), 4)
+            rep['cons_wait_full_frac'] = round(buf[2] / max(1, buf[4]), 4)
+            rep['cons_wait_handover_frac'] = round(buf[3] / max(1, buf[4]), 4)
+            rep['fin_idle_frac'] = round(buf[5] / max(1, buf[6]), 4)
+            items = max(1, int(buf[10]))
+            rep['fin_cycles_per_item'] = {k: round(float(buf[i]) / items) for k, i in
+                                          (('stage1', 7), ('pass2a', 8), ('reduce', 11), ('pass2b', 12), ('minmax2', 13), ('out', 9))}
+        print(name, label, json.dumps(rep), flush=True)
+        res[label] = rep
+    _lib.lib().dctd_fp_set_variant(0)
+    return res
 
 
 def main():
