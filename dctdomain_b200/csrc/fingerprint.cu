@@ -76,6 +76,7 @@ struct Layout {             // thread / shared-memory layout derived from (D, n,
 struct WsLayout {           // shared-memory layout of the warp-specialised kernel (fp_ws_kernel.cuh)
     int nst;                // TMA ring stages
     int DS;                 // pass-2a splits of the column range
+    int H;                  // pass-2a coefficient pairing: a thread owns k and k + H (H even)
     unsigned off_bars, off_meta, off_basis, off_desc, off_ring, off_u, off_ye, off_yo, off_f, off_tt, off_tm, off_mj;
     unsigned smem;
 };
@@ -837,7 +838,13 @@ WsLayout make_ws_layout(int m, int max_smem) {
     using Cfg = WsCfg<K, DC, RIDER>;
     WsLayout w{};
     const int N = K + 1, nk = m - 1;
-    w.DS = std::max(1, std::min(kWsFinThreads / nk, std::max(1, DC / 8 / 8)));
+    // pass 2a: a thread owns the coefficient pair (k, k + H); the columns are split over DS thread groups in whole
+    // octets of float4 steps.  DS = as many groups as the finisher threads allow, then lowered as long as the longest
+    // split does not grow (fewer partial sums to add up).
+    w.H = ((nk + 1) / 2 + 1) / 2 * 2;
+    const int OQ = std::max(1, DC / 64);
+    w.DS = std::max(1, std::min(kWsFinThreads / w.H, OQ));
+    while (w.DS > 1 && (OQ + w.DS - 2) / (w.DS - 1) == (OQ + w.DS - 1) / w.DS) --w.DS;
     size_t off = 0;
     auto take = [&](size_t bytes) { const size_t o = off; off += dctd::align_up(bytes, 128); return (unsigned)o; };
     w.off_bars = take((2 * kWsMaxStages + 4) * sizeof(unsigned long long));
@@ -857,6 +864,7 @@ WsLayout make_ws_layout(int m, int max_smem) {
     if (g_ws_stages > 0) nst = std::min<long long>(nst, g_ws_stages);
     nst = std::min<long long>(nst, kWsMaxStages);
     w.nst = nst >= 3 ? (int)nst : 0;
+    if (N * ((m + 1) / 2) * 2 > kWsFinThreads || w.H < 1) w.nst = 0;      // pass 2b runs as one pass of the finisher threads
     w.smem = (unsigned)(off + (size_t)std::max(w.nst, 0) * Cfg::STAGE_BYTES);
     return w;
 }

@@ -60,7 +60,7 @@ struct WsCfg {
 // per-role cycle counters (DCTD_FP_TIMING builds; scripts/fp_phases.py): one thread per role accumulates locally and
 // adds to Params::timing at exit.  Slots: 0 producer waiting for a free stage, 1 producer total, 2 consumer waiting
 // for a full stage, 3 consumer waiting for a free hand-over buffer, 4 consumer total, 5 finisher idle, 6 finisher
-// total, 7 finisher stage 1 (+ split / rider bookkeeping), 8 pass 2a, 9 output, 10 items, 11 reduce, 12 pass 2b, 13 row min-max.
+// total, 7 finisher stage 1 (+ split / rider bookkeeping), 8 pass 2a, 9 row min-max + output (warp 0), 10 items, 11 reduce, 12 pass 2b.
 #ifdef DCTD_FP_TIMING
 #define WS_T0() long long _wt = clock64()
 #define WS_ACC(var) do { const long long _n = clock64(); (var) += _n - _wt; _wt = _n; } while (0)
@@ -84,6 +84,13 @@ struct WsCfg {
 #define WS_WAIT(bar, par, site) do { if ((site) == 1 || (site) == 2) mbar_wait(bar, par); else mbar_wait_sleep(bar, par, (site) == 3 ? 256u : 96u); } while (0)
 #endif
 
+// read-only table lookup at a shared-memory byte address (the table never changes after the kernel prologue, so the
+// compiler may schedule these freely)
+__device__ __forceinline__ float lds_f32(unsigned int addr) {
+    float v;
+    asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
 __device__ __forceinline__ void lds_pk4(unsigned int addr, pk2 &lo, pk2 &hi) {
     asm volatile("ld.shared.v2.b64 {%0,%1}, [%2];" : "=l"(lo), "=l"(hi) : "r"(addr));
 }
@@ -114,8 +121,6 @@ __global__ void __launch_bounds__(WsCfg<K, DC, RIDER>::T, 1) fp_ws_kernel(const 
     double *Mj = reinterpret_cast<double *>(smem + wl.off_mj);             // [N][K] cos(pi (2j+1) k / 2n)
     __shared__ int u_slot[2];
     __shared__ int s_flag, s_last, s_rlast;
-    __shared__ double s_mn[kMaxN], s_mx[kMaxN];
-    __shared__ int s_bad[kMaxN];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int m = p.m, nk = m - 1;
@@ -423,7 +428,8 @@ __global__ void __launch_bounds__(WsCfg<K, DC, RIDER>::T, 1) fp_ws_kernel(const 
         // =============================== finishers ===============================
         const int ftid = tid - 32 * (1 + NCW);
         const int fwarp = ftid >> 5;
-        const int DS = wl.DS;
+        const int DS = wl.DS, H = wl.H;
+        const unsigned int tt_u32 = smem_u32(TT), tt_end = tt_u32 + 16u * D;
         double *Fp = Fs;                                   // [DS][N][nk]
         double *Fr = Fs + (size_t)DS * N * nk;             // [N][nk]
         double *Z = Fr + (size_t)N * nk;                   // [N][m]
@@ -468,39 +474,52 @@ __global__ void __launch_bounds__(WsCfg<K, DC, RIDER>::T, 1) fp_ws_kernel(const 
             }
         };
         // passes 2a / 2b, row min-max and the int8 output of one (domain, layer) whose Ye / Yo are ready
-        long long t_idle = 0, t_s1 = 0, t_2a = 0, t_rest = 0, t_red = 0, t_2b = 0, t_mm = 0;
-        (void)t_idle; (void)t_s1; (void)t_2a; (void)t_rest; (void)t_red; (void)t_2b; (void)t_mm;
+        long long t_idle = 0, t_s1 = 0, t_2a = 0, t_rest = 0, t_red = 0, t_2b = 0;
+        (void)t_idle; (void)t_s1; (void)t_2a; (void)t_rest; (void)t_red; (void)t_2b;
         WS_T0();
         auto finish_rest = [&](int dom_index, int layer) {
             WS_ACC(t_s1);
             // ---- pass 2a: F[j][k] = sum_{d < D/2} (e|o)[j][d] cos(pi (2d+1) k / 2D).  Cosines from the shared table
             //      TT[i] = cos(pi (i mod 4D) / 2D) at i = (2d+1) k (lanes hold consecutive k, the stride 2d+1 is odd:
             //      conflict-free), four columns per step at i + {0, 2k, 4k, 6k} (the table is extended by 8m entries, so
-            //      only i itself wraps); e / o are broadcast 16-byte loads ----
-            for (int w = ftid; w < nk * DS; w += NFT) {
-                const int k = 1 + w % nk, ds = w / nk;
+            //      only i itself wraps); e / o are broadcast 16-byte loads.  A thread owns two coefficients of the same
+            //      parity, k and k + H (H even), so that one load of e / o feeds both: the shared-memory pipe, which
+            //      also carries the TMA writes and the consumers' reads, is what bounds this pass ----
+            for (int w = ftid; w < H * DS; w += NFT) {
+                const int ds = w / H, ka = 1 + w % H;
+                if (ka > nk) continue;
+                const bool hasb = ka + H <= nk;
+                const int kb = hasb ? ka + H : ka;
                 // split boundaries in multiples of 8 quads (32 columns) when the width allows: no remainder loop
                 const int q0 = (HQ % 8 == 0) ? (HQ / 8 * ds / DS) * 8 : HQ * ds / DS;
                 const int q1 = (HQ % 8 == 0) ? (HQ / 8 * (ds + 1) / DS) * 8 : HQ * (ds + 1) / DS;
-                const float *yb = ((k & 1) ? Yo : Ye) + 4 * q0;
-                int idx = (int)(((long long)(8 * q0 + 1) * k) % (4LL * D));
-                const int s1 = 2 * k, s2 = 4 * k, s3 = 6 * k, s4 = 8 * k;
-                double f64[N];
+                const float *yb = ((ka & 1) ? Yo : Ye) + 4 * q0;
+                // table positions as shared-memory byte addresses: one add per lookup, no index scaling
+                unsigned int oa = tt_u32 + 4u * (unsigned int)(((long long)(8 * q0 + 1) * ka) % (4LL * D));
+                unsigned int ob = tt_u32 + 4u * (unsigned int)(((long long)(8 * q0 + 1) * kb) % (4LL * D));
+                const unsigned int sa = 8u * ka, sb = 8u * kb;      // 2k entries in bytes
+                double fa[N], fb[N];
 #pragma unroll
-                for (int j = 0; j < N; ++j) f64[j] = 0.0;
+                for (int j = 0; j < N; ++j) { fa[j] = 0.0; fb[j] = 0.0; }
                 const pk2 zero = pk(0.f, 0.f);
-                pk2 a[N][2];
+                pk2 aa[N][2], ab[N][2];
 #pragma unroll
-                for (int j = 0; j < N; ++j) { a[j][0] = zero; a[j][1] = zero; }
+                for (int j = 0; j < N; ++j) { aa[j][0] = zero; aa[j][1] = zero; ab[j][0] = zero; ab[j][1] = zero; }
                 auto quad = [&]() {
-                    const pk2 c01 = pk(TT[idx], TT[idx + s1]), c23 = pk(TT[idx + s2], TT[idx + s3]);
-                    idx += s4;
-                    if (idx >= 4 * D) idx -= 4 * D;
+                    const pk2 ca01 = pk(lds_f32(oa), lds_f32(oa + sa)), ca23 = pk(lds_f32(oa + 2 * sa), lds_f32(oa + 3 * sa));
+                    const pk2 cb01 = pk(lds_f32(ob), lds_f32(ob + sb)), cb23 = pk(lds_f32(ob + 2 * sb), lds_f32(ob + 3 * sb));
+                    oa += 4 * sa;
+                    if (oa >= tt_end) oa -= 16u * D;
+                    ob += 4 * sb;
+                    if (ob >= tt_end) ob -= 16u * D;
 #pragma unroll
                     for (int j = 0; j < N; ++j) {
                         const float4 v = *reinterpret_cast<const float4 *>(yb + j * half);
-                        a[j][0] = fma2(pk(v.x, v.y), c01, a[j][0]);
-                        a[j][1] = fma2(pk(v.z, v.w), c23, a[j][1]);
+                        const pk2 v01 = pk(v.x, v.y), v23 = pk(v.z, v.w);
+                        aa[j][0] = fma2(v01, ca01, aa[j][0]);
+                        aa[j][1] = fma2(v23, ca23, aa[j][1]);
+                        ab[j][0] = fma2(v01, cb01, ab[j][0]);
+                        ab[j][1] = fma2(v23, cb23, ab[j][1]);
                     }
                     yb += 4;
                 };
@@ -508,10 +527,13 @@ __global__ void __launch_bounds__(WsCfg<K, DC, RIDER>::T, 1) fp_ws_kernel(const 
 #pragma unroll
                     for (int j = 0; j < N; ++j) {
                         float l0, h0, l1, h1;
-                        unpk(a[j][0], l0, h0);
-                        unpk(a[j][1], l1, h1);
-                        f64[j] += (double)((l0 + h0) + (l1 + h1));
-                        a[j][0] = zero; a[j][1] = zero;
+                        unpk(aa[j][0], l0, h0);
+                        unpk(aa[j][1], l1, h1);
+                        fa[j] += (double)((l0 + h0) + (l1 + h1));
+                        unpk(ab[j][0], l0, h0);
+                        unpk(ab[j][1], l1, h1);
+                        fb[j] += (double)((l0 + h0) + (l1 + h1));
+                        aa[j][0] = zero; aa[j][1] = zero; ab[j][0] = zero; ab[j][1] = zero;
                     }
                 };
                 int q = q0;
@@ -525,10 +547,14 @@ __global__ void __launch_bounds__(WsCfg<K, DC, RIDER>::T, 1) fp_ws_kernel(const 
                     flush();
                 }
 #pragma unroll
-                for (int j = 0; j < N; ++j) Fp[((size_t)ds * N + j) * nk + (k - 1)] = f64[j];
+                for (int j = 0; j < N; ++j) {
+                    Fp[((size_t)ds * N + j) * nk + (ka - 1)] = fa[j];
+                    if (hasb) Fp[((size_t)ds * N + j) * nk + (kb - 1)] = fb[j];
+                }
             }
             fin_bar();
             WS_ACC(t_2a);
+            const bool layer_bad = s_flag != 0;       // read by everyone before thread 0 can start the next item
             for (int i = ftid; i < N * nk; i += NFT) {
                 double f = 0.0;
                 for (int ds = 0; ds < DS; ++ds) f += Fp[(size_t)ds * N * nk + i];
@@ -536,31 +562,46 @@ __global__ void __launch_bounds__(WsCfg<K, DC, RIDER>::T, 1) fp_ws_kernel(const 
             }
             fin_bar();
             WS_ACC(t_red);
-            // ---- pass 2b: Z[j][c] = sum_k cos(pi (2c+1) k / 2m) F[j][k], four interleaved float64 chains.  Lanes hold
-            //      consecutive c; walking k in lockstep would make the table stride 2(k+1) doubles between lanes (a 16- or
-            //      32-way bank conflict whenever k+1 is a multiple of 4 or 8), so every lane starts at its own k ----
-            for (int w = ftid; w < N * m; w += NFT) {
-                const int j = w / m, c = w % m;
-                const int stepc = 2 * c + 1;
-                const double *fr = Fr + j * nk;
-                int kk = lane % nk;
-                int idx = (int)(((long long)stepc * (kk + 1)) % (4 * m));
-                double z[4] = {0.0, 0.0, 0.0, 0.0};
-                auto term = [&](double &zz) {
-                    zz = fma(Tm[idx], fr[kk], zz);
-                    idx += stepc;
-                    if (idx >= 4 * m) idx -= 4 * m;
-                    if (++kk == nk) { kk = 0; idx = stepc; }
-                };
-                int it = 0;
-                for (; it + 4 <= nk; it += 4) { term(z[0]); term(z[1]); term(z[2]); term(z[3]); }
-                for (; it < nk; ++it) term(z[0]);
-                Z[w] = (z[0] + z[1]) + (z[2] + z[3]);
+            // ---- pass 2b: Z[j][c] = sum_k cos(pi (2c+1) k / 2m) F[j][k].  cos(pi (2(m-1-c)+1) k / 2m) =
+            //      (-1)^k cos(pi (2c+1) k / 2m), so columns c and m-1-c share their products: with E / O the sums over
+            //      the even / odd k, Z[c] = E + O and Z[m-1-c] = E - O.  Two adjacent lanes per column pair, one per
+            //      parity, two float64 chains each ----
+            {
+                const int MP = (m + 1) / 2;
+                const int w = ftid;                      // one pass: N * MP * 2 <= NFT is checked on the host
+                const bool act = w < N * MP * 2;
+                const int h = w & 1, t = act ? (w >> 1) : 0;
+                const int j = t / MP, c = t % MP;
+                double sum = 0.0;
+                if (act) {
+                    const int stepc = 2 * c + 1, step2 = 2 * stepc, m4 = 4 * m;
+                    const double *fr = Fr + j * nk;
+                    int k = h ? 1 : 2;
+                    int idx = stepc * k;                 // < 4m
+                    double z0 = 0.0, z1 = 0.0;
+                    for (; k + 2 <= nk; k += 4) {
+                        z0 = fma(Tm[idx], fr[k - 1], z0);
+                        idx += step2;
+                        if (idx >= m4) idx -= m4;
+                        z1 = fma(Tm[idx], fr[k + 1], z1);
+                        idx += step2;
+                        if (idx >= m4) idx -= m4;
+                    }
+                    if (k <= nk) z0 = fma(Tm[idx], fr[k - 1], z0);
+                    sum = z0 + z1;
+                }
+                const double other = __shfl_xor_sync(0xffffffffu, sum, 1);
+                if (act && h == 0) {
+                    Z[j * m + c] = sum + other;                              // E + O
+                    if (m - 1 - c != c) Z[j * m + (m - 1 - c)] = sum - other;   // E - O
+                }
             }
             fin_bar();
             WS_ACC(t_2b);
-            // ---- per-row min-max (one warp per row), *127, truncating int8 cast (fingerprint.py:193-195) ----
-            for (int j = fwarp; j < N; j += kWsFinWarps) {
+            // ---- per-row min-max, *127 and the truncating int8 cast (fingerprint.py:193-195): one warp per row, no
+            //      further CTA-level barrier; the other warps go ahead to the next item ----
+            if (fwarp < N) {
+                const int j = fwarp;
                 double mn = INFINITY, mx = -INFINITY;
                 int bad = 0;
                 for (int c = lane; c < m; c += 32) {
@@ -575,19 +616,14 @@ __global__ void __launch_bounds__(WsCfg<K, DC, RIDER>::T, 1) fp_ws_kernel(const 
                     mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
                     bad |= __shfl_xor_sync(0xffffffffu, bad, o);
                 }
-                if (lane == 0) { s_mn[j] = mn; s_mx[j] = mx; s_bad[j] = bad || !(mx > mn); }
+                const bool zero_row = layer_bad || bad || !(mx > mn);
+                int8_t *out = p.out + (int64_t)dom_index * p.out_stride + (int64_t)layer * (N * m) + j * m;
+                for (int c = lane; c < m; c += 32) {
+                    int qv = 0;
+                    if (!zero_row) qv = (int)(((Z[j * m + c] - mn) / (mx - mn)) * 127.0);
+                    out[c] = (int8_t)qv;
+                }
             }
-            fin_bar();
-            WS_ACC(t_mm);
-            const bool layer_bad = s_flag != 0;
-            int8_t *out = p.out + (int64_t)dom_index * p.out_stride + (int64_t)layer * (N * m);
-            for (int w = ftid; w < N * m; w += NFT) {
-                const int j = w / m;
-                int qv = 0;
-                if (!layer_bad && !s_bad[j]) qv = (int)(((Z[w] - s_mn[j]) / (s_mx[j] - s_mn[j])) * 127.0);
-                out[w] = (int8_t)qv;
-            }
-            fin_bar();      // s_flag / Z / s_mn are reused by the next finish
             WS_ACC(t_rest);
         };
 
@@ -683,7 +719,7 @@ __global__ void __launch_bounds__(WsCfg<K, DC, RIDER>::T, 1) fp_ws_kernel(const 
             else fin_bar();                                 // s_last / s_rlast are rewritten by the next iteration
         }
         WS_ACC(t_s1);
-        if (ftid == 0) { WS_PUT(5, t_idle); WS_PUT(6, t_idle + t_s1 + t_2a + t_rest + t_red + t_2b + t_mm); WS_PUT(7, t_s1); WS_PUT(8, t_2a); WS_PUT(9, t_rest);
-                          WS_PUT(11, t_red); WS_PUT(12, t_2b); WS_PUT(13, t_mm); }
+        if (ftid == 0) { WS_PUT(5, t_idle); WS_PUT(6, t_idle + t_s1 + t_2a + t_rest + t_red + t_2b); WS_PUT(7, t_s1); WS_PUT(8, t_2a); WS_PUT(9, t_rest);
+                          WS_PUT(11, t_red); WS_PUT(12, t_2b); }
     }
 }

@@ -15,7 +15,7 @@ NAMES = ['fetch', 'basis', 'stream', 'rider_handoff', 'meet', 'finish_total', 'r
          'fin_pass2a', 'fin_reduce', 'fin_pass2b', 'fin_minmax2', 'fin_out', '-']
 # warp-specialised kernel (fp_ws_kernel.cuh): one sampled thread per role, cycles summed over the CTAs
 WS_NAMES = ['prod_wait_free_stage', 'prod_total', 'cons_wait_full_stage', 'cons_wait_handover', 'cons_total', 'fin_idle',
-            'fin_total', 'fin_stage1', 'fin_pass2a', 'fin_out', 'items', 'fin_reduce', 'fin_pass2b', 'fin_minmax2']
+            'fin_total', 'fin_stage1', 'fin_pass2a', 'fin_out', 'items', 'fin_reduce', 'fin_pass2b']
 
 
 def run(name, plan, srcs, out):
@@ -40,7 +40,7 @@ def run(name, plan, srcs, out):
             rep['fin_idle_frac'] = round(buf[5] / max(1, buf[6]), 4)
             items = max(1, int(buf[10]))
             rep['fin_cycles_per_item'] = {k: round(float(buf[i]) / items) for k, i in
-                                          (('stage1', 7), ('pass2a', 8), ('reduce', 11), ('pass2b', 12), ('minmax2', 13), ('out', 9))}
+                                          (('stage1', 7), ('pass2a', 8), ('reduce', 11), ('pass2b', 12), ('minmax_out', 9))}
         print(name, label, json.dumps(rep), flush=True)
         res[label] = rep
     _lib.lib().dctd_fp_set_variant(0)

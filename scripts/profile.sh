@@ -10,7 +10,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv \
     --log-file gpurun_out/launches_$TAG.csv $CMD > gpurun_out/ncu_launches_$TAG.log 2>&1
 echo "launch list rc=$?"
 $CMD > gpurun_out/prof_plain2_$TAG.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:fp_kernel -s 4 -c 2 \
+ncu --set full --clock-control none --import-source on -k regex:fp_ws_kernel -s 4 -c 2 \
     -o gpurun_out/fp_$TAG -f $CMD > gpurun_out/ncu_fp_$TAG.log 2>&1
 echo "fp capture rc=$?"
 $CMD > gpurun_out/prof_plain3_$TAG.log 2>&1 &&

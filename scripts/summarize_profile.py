@@ -87,7 +87,7 @@ def to_bytes(s):
     return float(v) * {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9, 'Tbyte': 1e12}[u]
 
 
-for name, key in (('fp', 'fp_kernel'), ('l1', 'l1_scan_kernel')):
+for name, key in (('fp', 'fp_ws_kernel'), ('l1', 'l1_scan_kernel')):
     ks = summary.get(name + '_kernel')
     if ks:
         vals = [to_bytes(k['dram__bytes_read.sum']) + to_bytes(k['dram__bytes_write.sum']) for k in ks]
