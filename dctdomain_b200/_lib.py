@@ -60,6 +60,7 @@ def lib():
         'dctd_last_cuda_error_string': (C.c_char_p, []),
         'dctd_launch_count': (i64, [C.c_int]),
         'dctd_h2d_rows': (C.c_int, [vp, vp, i64, vp, vp, vp]),
+        'dctd_h2d_gather': (C.c_int, [vp, i64, vp]),
         'dctd_fp_plan_create': (C.c_int, [C.POINTER(FpGeometry), C.POINTER(vp)]),
         'dctd_fp_plan_destroy': (None, [vp]),
         'dctd_fp_workspace_bytes': (sz, [vp]),

@@ -41,6 +41,47 @@ int dctd_h2d_rows(const void *const *h_src, const int64_t *nbytes, int64_t n, vo
     return DCTD_OK;
 }
 
+/* The same staging as a gather KERNEL for host arrays the device can read (pinned memory): the SMs pull the pieces
+ * over PCIe with 16-byte loads, many pieces in flight, so the link stays busy across array boundaries (a DMA copy per
+ * array leaves a gap of a few microseconds between arrays).  d_table: n descriptors in device-accessible memory
+ * (pinned host memory or device memory), every src / dst / nbytes a multiple of 16. */
+namespace {
+__global__ void __launch_bounds__(256) gather_kernel(const dctd_copy_desc *__restrict__ table, long long n) {
+    for (long long e = blockIdx.x; e < n; e += gridDim.x) {
+        const dctd_copy_desc dsc = table[e];
+        const uint4 *src = reinterpret_cast<const uint4 *>(dsc.src);
+        uint4 *dst = reinterpret_cast<uint4 *>(dsc.dst);
+        const long long m = dsc.nbytes / 16;
+        constexpr int U = 8;
+        for (long long i0 = threadIdx.x; i0 < m; i0 += (long long)blockDim.x * U) {
+            uint4 v[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const long long i = i0 + (long long)u * blockDim.x;
+                if (i < m)
+                    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                                 : "=r"(v[u].x), "=r"(v[u].y), "=r"(v[u].z), "=r"(v[u].w)
+                                 : "l"(src + i));
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const long long i = i0 + (long long)u * blockDim.x;
+                if (i < m) dst[i] = v[u];
+            }
+        }
+    }
+}
+}  // namespace
+
+int dctd_h2d_gather(const dctd_copy_desc *d_table, int64_t n, void *stream) {
+    if (n < 0 || (n > 0 && !d_table)) return DCTD_ERR_ARG;
+    if (n == 0) return DCTD_OK;
+    const int grid = (int)(n < 148 * 8 ? n : 148 * 8);
+    gather_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_table, (long long)n);
+    DCTD_LAUNCH_CHECK();
+    return DCTD_OK;
+}
+
 int64_t dctd_launch_count(int reset) {
     int64_t v = dctd::g_launches;
     if (reset) dctd::g_launches = 0;

@@ -342,6 +342,114 @@ __global__ void __launch_bounds__((kWarps + 1) * 32, 1) l1_scan_kernel(const Sca
 }
 
 // ------------------------------------------------------------------------------------------
+// Thresholds for the streaming regime (nq <= 16) without a heap scan: every `red` adjacent lanes keep the
+// smallest distance they have seen per query over the sampled groups (every gstride-th group, direct
+// coalesced loads as in l1_thresh_stream_kernel).  Each of these M minima is the distance of a distinct real
+// vector, so the k-th smallest of them is >= the true k-th best distance: a valid threshold, and with M >> k
+// almost the k-th best of the sample itself.  l1_kth_kernel sorts the M <= 4096 values per query in shared
+// memory and writes the threshold key.
+// ------------------------------------------------------------------------------------------
+constexpr int kMinSlots = 4096;      // minima per query
+
+template <int TQ>
+__global__ void __launch_bounds__(128) l1_sample_min_kernel(const ScanParams p, unsigned int *mins, int red) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int C = chunks_of(p.d);
+    const int dpad = C * 16;
+    unsigned char *qs = smem;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    load_queries<1, TQ>(p, qs, 0, dpad);
+    __syncthreads();
+    const uint4 *qs4 = reinterpret_cast<const uint4 *>(qs);
+    unsigned int best[TQ];
+#pragma unroll
+    for (int a = 0; a < TQ; ++a) best[a] = 0xffffffffu;
+    constexpr int UC = 6;
+    const long long W = (long long)gridDim.x * (blockDim.x >> 5);
+    const long long gw = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
+    for (long long v = gw; v < p.n_groups; v += W) {          // n_groups = sampled groups here
+        const long long g = v * p.gstride;
+        const uint4 *gp = p.packed + g * C * 32 + lane;
+        unsigned int acc[TQ];
+#pragma unroll
+        for (int a = 0; a < TQ; ++a) acc[a] = 0u;
+        for (int c0 = 0; c0 < C; c0 += UC) {
+            uint4 dv[UC];
+#pragma unroll
+            for (int u = 0; u < UC; ++u) {
+                dv[u] = make_uint4(0x80808080u, 0x80808080u, 0x80808080u, 0x80808080u);
+                if (c0 + u < C) {
+                    const uint4 *src = gp + (size_t)(c0 + u) * 32;
+                    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                                 : "=r"(dv[u].x), "=r"(dv[u].y), "=r"(dv[u].z), "=r"(dv[u].w)
+                                 : "l"(src));
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < UC; ++u) {
+                if (c0 + u < C) {
+#pragma unroll
+                    for (int a = 0; a < TQ; ++a) {
+                        const uint4 qv = qs4[a * C + c0 + u];
+                        unsigned int sacc = acc[a];
+                        sacc = sad4(qv.x, dv[u].x, sacc);
+                        sacc = sad4(qv.y, dv[u].y, sacc);
+                        sacc = sad4(qv.z, dv[u].z, sacc);
+                        sacc = sad4(qv.w, dv[u].w, sacc);
+                        acc[a] = sacc;
+                    }
+                }
+            }
+        }
+        if (g * 32 + lane < p.n) {          // the padding lanes of the last group are not vectors
+#pragma unroll
+            for (int a = 0; a < TQ; ++a) best[a] = min(best[a], acc[a]);
+        }
+    }
+    // minimum over each run of `red` adjacent lanes (red = 1, 2, .., 32), one value per run
+    for (int o = 1; o < red; o <<= 1) {
+#pragma unroll
+        for (int a = 0; a < TQ; ++a) best[a] = min(best[a], __shfl_xor_sync(0xffffffffu, best[a], o));
+    }
+    if ((lane & (red - 1)) == 0) {
+        const long long slot = gw * (32 / red) + lane / red;
+        if (slot < kMinSlots) {
+#pragma unroll
+            for (int a = 0; a < TQ; ++a)
+                if (a < p.nq) mins[(long long)a * kMinSlots + slot] = best[a];
+        }
+    }
+}
+
+// one CTA per query: k-th smallest of the M minima -> thr_keys[q * k + k - 1] (largest id: ties pass the scan)
+__global__ void __launch_bounds__(256) l1_kth_kernel(const unsigned int *mins, int M, int k, unsigned long long *thr_keys,
+                                                     int *cnt) {
+    __shared__ unsigned int v[kMinSlots];
+    const long long qi = blockIdx.x;
+    int P = 64;
+    while (P < M) P <<= 1;
+    for (int i = threadIdx.x; i < P; i += blockDim.x) v[i] = (i < M) ? mins[qi * kMinSlots + i] : 0xffffffffu;
+    __syncthreads();
+    for (int k2 = 2; k2 <= P; k2 <<= 1) {
+        for (int j = k2 >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < (P >> 1); i += blockDim.x) {
+                const int lo = ((i & ~(j - 1)) << 1) | (i & (j - 1));
+                const int hi = lo | j;
+                const bool up = (lo & k2) == 0;
+                const unsigned int a = v[lo], b = v[hi];
+                if ((a > b) == up) { v[lo] = b; v[hi] = a; }
+            }
+            __syncthreads();
+        }
+    }
+    if (threadIdx.x == 0) {
+        cnt[qi] = 0;                        // candidate counter of the scan that follows
+        const unsigned int dk = (k <= M) ? v[k - 1] : 0xffffffffu;
+        thr_keys[qi * k + k - 1] = (dk == 0xffffffffu) ? kKeyMax : (((unsigned long long)dk << kIdBits) | kIdMask);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // threshold scan: every vector whose distance is <= the query's threshold (k-th best of a sample of
 // the database, an upper bound of the true k-th best) is appended to the query's candidate list in
 // global memory.  No per-warp selection state: the scan is SADs + one compare per pair.
@@ -699,7 +807,10 @@ struct TopkPlan {
     long long gstride;
     ThreshConfig tc;
     int cmax;
-    size_t off_parts_full, off_parts_samp, off_tmp, off_thr, off_cnt, off_flags, off_cand, total;
+    size_t off_parts_full, off_parts_samp, off_tmp, off_thr, off_cnt, off_flags, off_cand, off_mins, total;
+    // streaming regime: thresholds from lane minima (l1_sample_min_kernel) instead of a heap scan of the sample
+    long long samp_groups;   // sampled groups
+    int samp_grid, samp_red, samp_m;   // CTAs of 4 warps, lanes per minimum, minima per query
 };
 
 constexpr int kCmax = 8192;  // candidate slots per query (threshold path)
@@ -738,6 +849,16 @@ bool make_plan(long long nq, long long n, int d, int k, TopkPlan *pl) {
             pl->tc = tc;
             pl->thresh = true;
         }
+        if (pl->thresh && tc.stream) {
+            // one warp per sampled group up to 8 CTAs of 4 warps per SM; as many minima per query as fit
+            pl->samp_groups = sg;
+            const long long warps = std::min<long long>(sg, kSMs * 8 * 4);
+            pl->samp_grid = (int)((warps + 3) / 4);
+            int red = 1;
+            while ((long long)pl->samp_grid * 4 * (32 / red) > kMinSlots && red < 32) red <<= 1;
+            pl->samp_red = red;
+            pl->samp_m = (int)std::min<long long>((long long)pl->samp_grid * 4 * (32 / red), kMinSlots);
+        }
     }
     size_t off = 0;
     auto take = [&](size_t bytes) { const size_t o = off; off += dctd::align_up(bytes, 256); return o; };
@@ -753,6 +874,7 @@ bool make_plan(long long nq, long long n, int d, int k, TopkPlan *pl) {
         pl->off_cnt = take((size_t)nq * sizeof(int));
         pl->off_flags = take((size_t)nq * sizeof(int));
         pl->off_cand = take((size_t)nq * (size_t)pl->cmax * 8);
+        pl->off_mins = pl->tc.stream ? take((size_t)16 * kMinSlots * sizeof(unsigned int)) : 0;
     }
     pl->off_tmp = take(tmp_parts * list);
     pl->total = off + 256;
@@ -822,7 +944,7 @@ int run_merge(const unsigned long long *keys, long long parts, long long nq, int
     return DCTD_OK;
 }
 
-int g_l1_mode = 0;   // tuning / test hook: 0 = automatic, 1 = force the heap scan, see dctd_l1_set_mode
+int g_l1_mode = 0;   // tuning / test hook: 0 = automatic, 1 = force the heap scan, 2 = heap-scan thresholds in the streaming regime
 
 }  // namespace
 
@@ -900,8 +1022,21 @@ int dctd_l1_topk(const int8_t *d_q, int64_t nq, const void *d_packed, int64_t n,
     int *cnt = (int *)(ws + pl.off_cnt);
     int *flags = (int *)(ws + pl.off_flags);
     unsigned long long *cand = (unsigned long long *)(ws + pl.off_cand);
-    // 1. thresholds: exact top-k of every gstride-th group
-    {
+    // 1. thresholds: from lane minima over every gstride-th group (few queries), or the exact top-k of that sample
+    if (pl.tc.stream && g_l1_mode != 2) {
+        ScanParams s1 = sp;
+        s1.gstride = pl.gstride;
+        s1.n_groups = pl.samp_groups;
+        unsigned int *mins = (unsigned int *)(ws + pl.off_mins);
+        typedef void (*MinFn)(const ScanParams, unsigned int *, int);
+        const int tq = pl.tc.tq;
+        MinFn fn = tq == 4 ? l1_sample_min_kernel<4> : (tq == 8 ? l1_sample_min_kernel<8> : l1_sample_min_kernel<16>);
+        // every slot below samp_m is written (lanes that saw no vector write 0xffffffff = "no bound")
+        fn<<<pl.samp_grid, 128, pl.tc.smem, stream>>>(s1, mins, pl.samp_red);
+        DCTD_LAUNCH_CHECK();
+        l1_kth_kernel<<<(unsigned)nq, 256, 0, stream>>>(mins, pl.samp_m, k, thr, cnt);
+        DCTD_LAUNCH_CHECK();
+    } else {
         ScanParams s1 = sp;
         s1.parts = parts_samp;
         s1.gstride = pl.gstride;
@@ -911,7 +1046,7 @@ int dctd_l1_topk(const int8_t *d_q, int64_t nq, const void *d_packed, int64_t n,
         if (rc != DCTD_OK) return rc;
     }
     // 2. one pass over the database: append everything within the threshold
-    DCTD_CUDA_TRY(cudaMemsetAsync(cnt, 0, (size_t)nq * sizeof(int), stream));
+    if (!(pl.tc.stream && g_l1_mode != 2)) DCTD_CUDA_TRY(cudaMemsetAsync(cnt, 0, (size_t)nq * sizeof(int), stream));
     {
         ScanParams s2 = sp;
         s2.thr_keys = thr; s2.cand = cand; s2.cnt = cnt; s2.cmax = pl.cmax;

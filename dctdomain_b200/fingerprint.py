@@ -128,15 +128,37 @@ def execute_plan(plan: _Plan, src_tensors, out: torch.Tensor, tables_resident=Fa
 
 
 def _host_f32(x):
-    """numpy / CPU torch [rows, D] -> (keep-alive object, address, rows, D) of contiguous float32 host memory."""
+    """numpy / CPU torch [rows, D] -> (keep-alive object, address, rows, D, pinned) of contiguous float32 host memory."""
     if isinstance(x, torch.Tensor):
         t = x if (x.dtype == torch.float32 and x.is_contiguous()) else x.to(torch.float32).contiguous()
-        return t, t.data_ptr(), int(t.shape[0]), int(t.shape[1])
+        return t, t.data_ptr(), int(t.shape[0]), int(t.shape[1]), t.is_pinned()
     a = np.ascontiguousarray(x, dtype=np.float32)
-    return a, a.ctypes.data, int(a.shape[0]), int(a.shape[1])
+    return a, a.ctypes.data, int(a.shape[0]), int(a.shape[1]), False
+
+
+_GATHER_PIECE = 256 << 10      # bytes per piece of the gather kernel's work list
+_tables: dict = {}
+
+
+def _pinned_table(device, n_entries: int) -> np.ndarray:
+    """Pinned host array [n_entries, 3] of int64 (src, dst, nbytes descriptors the gather kernel reads over PCIe)."""
+    t = _tables.get(device)
+    if t is None or t.shape[0] < n_entries:
+        t = torch.empty((max(n_entries, 4096) * 2, 3), dtype=torch.int64).pin_memory()
+        _tables[device] = t
+    return t
 
 
 _stage: dict = {}
+_aux: dict = {}
+
+
+def _aux_stream(device) -> torch.cuda.Stream:
+    st = _aux.get(device)
+    if st is None:
+        st = torch.cuda.Stream(device=device)
+        _aux[device] = st
+    return st
 
 
 def _stage_buffer(device, nbytes):
@@ -147,7 +169,7 @@ def _stage_buffer(device, nbytes):
     return buf
 
 
-def quantize_batch(fps, qdim=(3, 80, 3, 80), device=None, maxlen=DEFAULT_MAXLEN, overlap=OVERLAP):
+def quantize_batch(fps, qdim=(3, 80, 3, 80), device=None, maxlen=DEFAULT_MAXLEN, overlap=OVERLAP, _timing=None):
     """``quantize`` for a list of Fingerprint-like objects in one kernel launch per (n, m) group.
 
     Each object needs ``embed`` ({layer: [L, D] array | list of window arrays}), ``domains`` (list of
@@ -169,13 +191,18 @@ def quantize_batch(fps, qdim=(3, 80, 3, 80), device=None, maxlen=DEFAULT_MAXLEN,
     # ---- sources: device pointer per (layer, source); host arrays are staged ----
     ptr = [[] for _ in range(n_layers)]        # device addresses (staged ones are offsets until the copy)
     staged = [[] for _ in range(n_layers)]     # True where ptr holds an offset into the staging buffer
-    keep, h_addr, h_bytes, h_off = [], [], [], []
+    keep, h_addr, h_bytes, h_off, h_pin = [], [], [], [], []
     src_rows, prot_src0, prot_nsrc, prot_len = [], [], [], []
     D = None
     stage_bytes = 0
-    stream = torch.cuda.current_stream(dev).cuda_stream
+    main_stream = torch.cuda.current_stream(dev)
+    stream = main_stream.cuda_stream
+    # host arrays arrive as many separate allocations; they are staged on a side stream (batched submission,
+    # dctd_h2d_rows) while this thread keeps walking the batch, the compute stream joins before the kernel
+    aux_stream = _aux_stream(dev)
+    aux_stream.wait_stream(main_stream)
     have = _stage.get(dev)            # staging buffer of an earlier call (kept alive until this call returns)
-    state = {'done': 0, 'bases': []}  # bases: [(first h index, device address that h_off is relative to)]
+    state = {'done': 0, 'bases': [], 'tab': 0}  # bases: [(first h index, device address that h_off is relative to)]
 
     def flush(final=False):
         """Issues the H2D copies collected so far.  While the staging buffer of an earlier call is large enough
@@ -198,12 +225,29 @@ def quantize_batch(fps, qdim=(3, 80, 3, 80), device=None, maxlen=DEFAULT_MAXLEN,
         a_len = np.array(h_bytes[lo:], dtype=np.int64)
         a_off = np.array(h_off[lo:], dtype=np.int64)
         with torch.cuda.device(dev):
-            _lib.check(L.dctd_h2d_rows(a_src.ctypes.data, a_len.ctypes.data, len(a_src), base,
-                                       a_off.ctypes.data, stream), 'dctd_h2d_rows')
+            if all(h_pin[lo:]) and not (a_len % 16).any():
+                # pinned sources: one gather kernel over <= 256 KB pieces (no per-array DMA gaps)
+                npc = (a_len + _GATHER_PIECE - 1) // _GATHER_PIECE
+                total = int(npc.sum())
+                owner = np.repeat(np.arange(len(a_len)), npc)
+                first = np.cumsum(npc) - npc
+                within = (np.arange(total) - first[owner]) * _GATHER_PIECE
+                t0 = state['tab']
+                table = _pinned_table(dev, t0 + total)
+                view = table.numpy()[t0:t0 + total]
+                view[:, 0] = a_src[owner].astype(np.int64) + within
+                view[:, 1] = base + a_off[owner] + within
+                view[:, 2] = np.minimum(a_len[owner] - within, _GATHER_PIECE)
+                state['tab'] = t0 + total
+                keep.append(table)
+                _lib.check(L.dctd_h2d_gather(table.data_ptr() + t0 * 24, total, aux_stream.cuda_stream), 'dctd_h2d_gather')
+            else:
+                _lib.check(L.dctd_h2d_rows(a_src.ctypes.data, a_len.ctypes.data, len(a_src), base,
+                                           a_off.ctypes.data, aux_stream.cuda_stream), 'dctd_h2d_rows')
         state['done'] = len(h_addr)
 
     for fi, fp in enumerate(fps):
-        if fi % 32 == 31:
+        if fi % 32 == 31 or fi in (2, 8):       # start the DMA early, then keep it fed
             flush()
         if len(fp.embed) != n_layers:
             raise ValueError('all proteins of a batch must carry the same layers')
@@ -230,8 +274,9 @@ def quantize_batch(fps, qdim=(3, 80, 3, 80), device=None, maxlen=DEFAULT_MAXLEN,
                 else:
                     if np.ndim(w) != 2:
                         raise ValueError('embeddings must be [rows, D]')
-                    obj, addr, r, dd = _host_f32(w)
+                    obj, addr, r, dd, pinned = _host_f32(w)
                     keep.append(obj)
+                    h_pin.append(pinned)
                     h_addr.append(addr)
                     h_bytes.append(r * dd * 4)
                     h_off.append(stage_bytes)
@@ -250,6 +295,13 @@ def quantize_batch(fps, qdim=(3, 80, 3, 80), device=None, maxlen=DEFAULT_MAXLEN,
         prot_len.append(rows0[0] if nwin == 1 else (nwin - 1) * (maxlen - overlap) + rows0[-1])
 
     flush(final=True)
+    main_stream.wait_stream(aux_stream)
+    if _timing is not None:                 # debug hook (scripts/e2e_phases.py): host time stamps of the call's phases
+        import time as _t
+        _timing['walk_done'] = _t.perf_counter()
+        ev = torch.cuda.Event()
+        ev.record(main_stream)
+        _timing['copies_event'] = ev
     if h_addr:
         def resolve(hi):
             base = state['bases'][-1][1] if hi >= state['bases'][-1][0] else state['bases'][0][1]
@@ -290,18 +342,26 @@ def quantize_batch(fps, qdim=(3, 80, 3, 80), device=None, maxlen=DEFAULT_MAXLEN,
                 _lib.check(L.dctd_fp_execute(plan.handle, ptrs.ctypes.data, D, out.data_ptr(), out.stride(0),
                                              ws.data_ptr(), ws.numel(), 0, stream), 'dctd_fp_execute')
             outs.append((out, n * m, lids, plan))
+        if _timing is not None:
+            _timing['launched'] = _t.perf_counter()
+            _timing['copies_event'].synchronize()
+            _timing['copies_done'] = _t.perf_counter()
         for out, nm, lids, _plan in outs:
             arr = out.cpu().numpy()
             for pos, li in enumerate(lids):
                 blocks[li] = arr[:, pos * nm:(pos + 1) * nm]
 
+    if _timing is not None:
+        _timing['results_on_host'] = _t.perf_counter()
     # ---- quants dicts, same update order as src/fingerprint.py:184-201 ----
+    # the reference's values are int64 arrays of n*m entries per layer, layer after layer (fingerprint.py:194-200)
+    wide = np.concatenate([blocks[li] for li in range(n_layers)], axis=1).astype(np.int64) if dom_prot else None
     for pi, fp in enumerate(fps):
         mine = entries[pi]
         simple = not fp.quants and len({kept for kept, _ in mine}) == len(mine)
-        if simple:      # the usual case: fresh object, every domain listed once
+        if simple:      # the usual case: fresh object, every domain listed once (rows of one widened block)
             for kept, row in mine:
-                fp.quants[kept] = np.concatenate([blocks[li][row] for li in range(n_layers)]).astype(np.int64)
+                fp.quants[kept] = wide[row]
         else:
             for li in range(n_layers):
                 for kept, row in mine:

@@ -46,6 +46,16 @@ int64_t dctd_launch_count(int reset);
 int dctd_h2d_rows(const void *const *h_src, const int64_t *nbytes, int64_t n, void *d_base,
                   const int64_t *d_off, void *stream);
 
+/* The same staging for host arrays that the device can read directly (pinned memory): one gather kernel pulls all
+ * pieces over PCIe instead of one DMA copy per array.  d_table: n descriptors in device-accessible memory (pinned
+ * host or device memory); src, dst and nbytes of every piece must be multiples of 16. */
+typedef struct dctd_copy_desc {
+    const void *src; /* device-accessible source (pinned host memory) */
+    void *dst;       /* device destination */
+    int64_t nbytes;
+} dctd_copy_desc;
+int dctd_h2d_gather(const dctd_copy_desc *d_table, int64_t n, void *stream);
+
 /* =====================================================================================
  * Hot path 1: DCT fingerprints ("quant2D")
  *   replaces reference src/fingerprint.py:110-201 (scale / idct_quant / get_doms / quantize)
