@@ -55,21 +55,31 @@ def _cpu_task(i):
     return int(q[f'1-{L}'].sum())
 
 
-def cpu_fingerprint_rate(n_domains: int, cores: int, repeat_pool: int = 64):
-    """domains/s of the faithful oracle port on `cores` processes.  Workers are forked after the
-    inputs exist (no pickling of embeddings, which the reference does pay: make_db.py:48-49)."""
-    import multiprocessing as mp
-    import synth
-    global _CPU_EMB
-    lens = batch_lengths(12345, min(n_domains, repeat_pool))
-    _CPU_EMB = [synth.layers(900 + i, int(L), D, 'white') for i, L in enumerate(lens)]
-    ctx = mp.get_context('fork')
-    with ctx.Pool(cores) as pool:
-        pool.map(_cpu_task, range(cores))                      # warm the workers
+class CpuArm:
+    """The reference's CPU path: the faithful oracle port of fingerprint.py quantize under
+    multiprocessing.Pool(cores), the `make_db.py --cpu N` pattern (src/make_db.py:48-49).  The pool and the input
+    embeddings are created once (workers are forked after the inputs exist: no pickling of embeddings, which the
+    reference does pay); `rate(n)` times one pool.map over n domains."""
+
+    def __init__(self, cores: int, distinct: int = 64):
+        import multiprocessing as mp
+        import synth
+        global _CPU_EMB
+        lens = batch_lengths(12345, distinct)
+        _CPU_EMB = [synth.layers(900 + i, int(L), D, 'white') for i, L in enumerate(lens)]
+        self.cores = cores
+        self.pool = mp.get_context('fork').Pool(cores)
+        self.pool.map(_cpu_task, range(cores))                  # warm the workers
+
+    def rate(self, n_domains: int):
         t0 = time.perf_counter()
-        pool.map(_cpu_task, range(n_domains), chunksize=1)
+        self.pool.map(_cpu_task, range(n_domains), chunksize=1)
         dt = time.perf_counter() - t0
-    return n_domains / dt, dt
+        return n_domains / dt, dt
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
 
 
 def run_reference(args):
@@ -77,14 +87,16 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    r0, _ = cpu_fingerprint_rate(max(cores * 2, 16), cores)           # calibration, untimed
-    budget_s = 60.0 / max(1, args.steps + args.warmup)                # whole run ~1 minute
+    arm = CpuArm(cores)
+    r0, _ = arm.rate(max(cores * 2, 16))                              # calibration, untimed
+    budget_s = 90.0 / max(1, args.steps + args.warmup)                # whole run ~1.5 minutes
     per_step = int(min(max(r0 * min(budget_s, 3.0), cores * 2), 5000))
     rates = []
     for s in range(args.warmup + args.steps):
-        r, dt = cpu_fingerprint_rate(per_step, cores)
+        r, dt = arm.rate(per_step)
         if s >= args.warmup:
             rates.append((r, dt))
+    arm.close()
     total_t = sum(dt for _, dt in rates)
     value = per_step * len(rates) / total_t
     sample = (f'{per_step} domains per step, L~U{{{LMIN}..{LMAX}}}, {LAYERS}x{D} fp32, oracle port of '
@@ -321,9 +333,11 @@ def run_ours(args):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cores = os.cpu_count() or 1
-        r0, _ = cpu_fingerprint_rate(max(cores * 2, 16), cores)       # calibration
+        arm = CpuArm(cores)
+        r0, _ = arm.rate(max(cores * 2, 16))                          # calibration
         n = int(min(max(r0 * 12.0, cores * 4), 20000))                # ~12 s of CPU work
-        r, dt = cpu_fingerprint_rate(n, cores)
+        r, dt = arm.rate(n)
+        arm.close()
         if search is not None:
             search['cpu_baseline'] = cpu_search_rate(cores)
         cpu = {'value': r, 'unit': 'fingerprints/s', 'cores': cores, 'kind': 'port', 'seconds': dt,

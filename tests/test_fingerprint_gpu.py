@@ -113,6 +113,37 @@ def test_cuda_tensors_consumed_in_place_and_batch_equals_single():
         assert np.array_equal(a.quants[d], me.quants[d])
 
 
+def test_pinned_host_arrays_take_the_gather_path_and_match():
+    """Pinned torch tensors are staged by the gather kernel (dctd_h2d_gather), numpy arrays by one DMA copy each
+    (dctd_h2d_rows); mixed batches fall back to the copies.  Same bytes on every route, windows included."""
+    from dctdomain_b200.fingerprint import Fingerprint, quantize_batch
+    st = cases.STITCH_CASES[0]
+    chunks = cases.stitch_chunks_for(st)
+    inputs = [(c, synth.layers(c['seed'], c['L'], c['D'], c['kind'])) for c in (cases.FP_CASES[0], cases.FP_CASES[3])]
+    inputs.append((st, {lay: [c[lay] for c in chunks] for lay in (15, 21)}))
+
+    def conv(a, pin):
+        if isinstance(a, (list, tuple)):
+            return [conv(x, pin) for x in a]
+        return torch.from_numpy(np.ascontiguousarray(a)).pin_memory() if pin else a
+
+    def run(kind):
+        fps = []
+        for i, (c, emb) in enumerate(inputs):
+            pin = kind == 'pinned' or (kind == 'mixed' and i % 2 == 0)
+            fps.append(Fingerprint(pid=c['name'], seq='A' * c['L'], embed={k: conv(v, pin) for k, v in emb.items()},
+                                   domains=list(c['domains']), quants={}))
+        quantize_batch(fps, [3, 80, 3, 80], maxlen=st['maxlen'])
+        return fps
+
+    ref = run('numpy')
+    for kind in ('pinned', 'mixed'):
+        for a, b in zip(ref, run(kind)):
+            assert a.domains == b.domains
+            for d in a.domains:
+                assert np.array_equal(a.quants[d], b.quants[d]), (kind, a.pid, d)
+
+
 def test_properties_at_full_size():
     """Size-independent properties on a batch of configs[1]-sized domains: each 80-byte row holds exactly
     the values 0 and 127 (min-max), the result is invariant to a per-column offset and a positive scale of

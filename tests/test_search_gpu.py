@@ -228,6 +228,23 @@ def test_threshold_path_overflow_falls_back_to_heap_scan():
     _check(q[:7], db, 20)                           # streaming kernel + fallback
 
 
+@pytest.mark.parametrize('order', ['ascending', 'descending'])
+def test_streaming_thresholds_on_sorted_database_with_ragged_tail(order):
+    """Few queries take the streaming path whose thresholds come from lane minima over every 32nd group: a database
+    sorted by distance to the query (the worst case for a strided sample), a size that is not a multiple of 32 (the
+    padding lanes of the last group must not produce minima) and a k above the per-warp sample."""
+    rs = np.random.RandomState(11)
+    n = 70_000 + 17
+    q = rs.randint(0, 128, size=(3, 480)).astype(np.int8)
+    db = rs.randint(0, 128, size=(n, 480)).astype(np.int8)
+    db[: n // 2] = np.clip(q[0].astype(int) + rs.randint(-20, 21, size=(n // 2, 480)), 0, 127).astype(np.int8)
+    dist = np.abs(db.astype(np.int32) - q[0].astype(np.int32)).sum(axis=1)
+    perm = np.argsort(dist, kind='stable')
+    db = db[perm if order == 'ascending' else perm[::-1]]
+    _check(q, db, 50)
+    _check(q[:1], db, 256)
+
+
 def test_threshold_and_heap_paths_agree_at_scale():
     from dctdomain_b200 import _lib
     db = synth.fingerprints(53, 400_000)
