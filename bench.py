@@ -199,6 +199,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
+        os.environ['NCCL_DEBUG'] = os.environ.get('DCTD_NCCL_DEBUG', 'WARN')    # stdout carries exactly one JSON line
         dist.init_process_group('nccl', device_id=dev)
 
     def barrier():
