@@ -981,6 +981,13 @@ int dctd_fp_plan_create(const dctd_fp_geometry *geo, dctd_fp_plan **out_plan) {
             }
         };
 
+        // rows a run of pieces reads: a row averaged from two windows is two distinct rows of input
+        auto piece_rows_read = [&](int32_t off, int32_t n) {
+            int64_t r = 0;
+            for (int32_t i = 0; i < n; ++i) r += (int64_t)pl->pieces[off + i].nrows * (pl->pieces[off + i].src_b >= 0 ? 2 : 1);
+            return r;
+        };
+
         // ---- validation + fusion analysis: a protein whose batch holds its global domain (one segment
         //      covering every row) next to other, pairwise disjoint domains reads each row once: the other
         //      domains' items carry the global fingerprint along ("rider"), the global domain itself only
@@ -1059,7 +1066,7 @@ int dctd_fp_plan_create(const dctd_fp_geometry *geo, dctd_fp_plan **out_plan) {
             n_counters += geo->n_layers;
             pl->doms[i] = di;
             rider_next[i] = n_fill;
-            pl->algo_bytes += (int64_t)geo->n_layers * geo->D * 4 * [&] { int64_t r = 0; for (auto &rg : filler[p]) r += rg.second - rg.first; return r; }();
+            pl->algo_bytes += (int64_t)geo->n_layers * geo->D * 4 * piece_rows_read(di.piece_off, di.n_pieces);
             for (int layer = 0; layer < geo->n_layers; ++layer) {
                 int slot = 0;
                 for (int pi = 0; pi < di.n_pieces; ++pi) {
@@ -1098,7 +1105,7 @@ int dctd_fp_plan_create(const dctd_fp_geometry *geo, dctd_fp_plan **out_plan) {
                 n_counters += geo->n_layers;
             }
             pl->doms[i] = di;
-            pl->algo_bytes += (int64_t)geo->n_layers * l0 * geo->D * 4;
+            pl->algo_bytes += (int64_t)geo->n_layers * geo->D * 4 * piece_rows_read(di.piece_off, di.n_pieces);
             const int rps = (int)((l0 + di.nsplit - 1) / di.nsplit);
             const int ride0 = gdom >= 0 ? rider_next[gdom] : 0;
             if (gdom >= 0) { rider_next[gdom] += di.nsplit; pl->has_rider = true; }

@@ -100,7 +100,8 @@ int dctd_fp_plan_create(const dctd_fp_geometry *geo, dctd_fp_plan **out_plan);
 void dctd_fp_plan_destroy(dctd_fp_plan *plan);
 /* bytes of device workspace dctd_fp_execute needs for this plan */
 size_t dctd_fp_workspace_bytes(const dctd_fp_plan *plan);
-/* algorithmic input bytes of the plan: sum over domains of n_layers * L * D * 4 (roofline numerator) */
+/* algorithmic input bytes of the plan (roofline numerator): n_layers * D * 4 per row read - every row of every
+ * domain once (rows shared with a riding global fingerprint once, rows averaged from two windows twice) */
 int64_t dctd_fp_algorithmic_bytes(const dctd_fp_plan *plan);
 int32_t dctd_fp_num_items(const dctd_fp_plan *plan);
 

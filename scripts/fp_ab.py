@@ -84,6 +84,49 @@ def proteins(n_prot, D, variants, res):
     ab(f'proteins_{n_prot}x{D}_fused', plan, srcs, out, 2 * total * D * 4, variants, res)
 
 
+def windows(n_prot, D, variants, res, maxlen=500, overlap=200):
+    """configs[2]: long proteins delivered as maxlen windows (stride maxlen - overlap, rows in two windows averaged
+    in-kernel), 3-12 contiguous domains + the global one per protein."""
+    rs = np.random.RandomState(0)
+    stride = maxlen - overlap
+    plens = rs.randint(501, 4001, size=n_prot)
+    src_rows, prot_src0, prot_nsrc = [], [], []
+    for Lp in plens:
+        prot_src0.append(len(src_rows))
+        n = 0
+        start = 0
+        while True:
+            rows = min(maxlen, Lp - start)
+            if start > 0 and rows <= overlap:
+                break
+            src_rows.append(rows)
+            n += 1
+            if start + rows >= Lp:
+                break
+            start += stride
+        prot_nsrc.append(n)
+        # the reference drops a last window of <= 200 rows: the protein then ends with the previous window
+    plens_eff = [(prot_nsrc[i] - 1) * stride + src_rows[prot_src0[i] + prot_nsrc[i] - 1] for i in range(n_prot)]
+    total = int(sum(src_rows))
+    torch.manual_seed(0)
+    layers = [torch.randn(total, D, device='cuda') for _ in range(2)]
+    off = np.concatenate([[0], np.cumsum(src_rows)])
+    srcs = [[layers[l][off[i]:off[i + 1]] for i in range(len(src_rows))] for l in range(2)]
+    dom_prot, sb, se = [], [], []
+    for p, Lp in enumerate(plens_eff):
+        k = rs.randint(3, 13)
+        cuts = np.sort(rs.choice(np.arange(30, Lp - 30, 10), size=k - 1, replace=False))
+        edges = [0] + [int(c) for c in cuts] + [int(Lp)]
+        for a, b in zip(edges[:-1], edges[1:]):
+            dom_prot.append(p); sb.append(a); se.append(b)
+        dom_prot.append(p); sb.append(0); se.append(int(Lp))
+    nd = len(dom_prot)
+    plan = make_plan(2, D, 3, 80, src_rows, prot_src0, prot_nsrc, dom_prot, list(range(nd + 1)), sb, se,
+                     maxlen=maxlen, overlap=overlap)
+    out = torch.empty((nd, 480), dtype=torch.int8, device='cuda')
+    ab(f'windows_{n_prot}x{D}_L501-4000', plan, srcs, out, 2 * total * D * 4, variants, res)
+
+
 def main():
     n_dom = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
     caps = [int(v) for v in sys.argv[2].split(',')] if len(sys.argv) > 2 else [0]
@@ -94,6 +137,7 @@ def main():
     proteins(n_dom // 2, 1280, variants, res)
     domains(n_dom, 640, variants, res)
     domains(n_dom * 2, 1280, variants, res, lo=40, hi=120)
+    windows(max(64, n_dom // 8), 1280, variants, res)
     os.makedirs('gpurun_out', exist_ok=True)
     json.dump(res, open('gpurun_out/fp_ab.json', 'w'), indent=1)
 
