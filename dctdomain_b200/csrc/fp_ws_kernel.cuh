@@ -49,7 +49,11 @@ struct WsCfg {
     static constexpr int KS = RIDER ? 2 * K : K;
     static constexpr int NCT = DC / 4;                  // consumer threads: one per float4 column group
     static constexpr int NCW = NCT / 32;
-    static constexpr int R = (5120 / DC) < 2 ? 2 : ((5120 / DC) > 8 ? 8 : (5120 / DC));   // rows per stage
+#ifndef WS_STAGE_ROW_BYTES
+#define WS_STAGE_ROW_BYTES 5120
+#endif
+    static constexpr int R0 = WS_STAGE_ROW_BYTES / DC / 2 * 2;
+    static constexpr int R = R0 < 2 ? 2 : (R0 > 8 ? 8 : R0);   // rows per stage (even)
     static constexpr int T = 32 * (1 + NCW + kWsFinWarps);
     static constexpr int STAGE_BYTES = R * DC * 4;
     static constexpr int FLUSH_EVERY = (8 / R) < 1 ? 1 : (8 / R);
