@@ -256,3 +256,88 @@ def test_protein_level_fusion_on_and_off():
         w = np.array([want[d] for d in a.domains])
         _compare('fusion/on/' + a.pid, ga, w, 0.01)
         _compare('fusion/off/' + a.pid, gb, w, 0.01)
+
+
+@pytest.mark.parametrize('seed', [0, 1, 2, 3])
+@pytest.mark.parametrize('D', [1280, 640])
+def test_geometry_fuzz_warp_specialised_vs_general_kernel(seed, D):
+    """Random batch geometry - short and long proteins, maxlen windows, discontinuous / overlapping / unsorted
+    domains, global domains with and without fusion partners, domains long enough to be split over items - run through
+    the warp-specialised kernel and the general one (dctd_fp_set_variant(9)).  The two differ only in float32 chain
+    lengths: at most 1 LSB on a handful of bytes; and each kernel is bit-reproducible from launch to launch (its
+    summation orders are fixed, whatever the scheduling of the persistent CTAs)."""
+    from dctdomain_b200 import _lib
+    from dctdomain_b200.fingerprint import execute_plan, make_plan
+    rs = np.random.RandomState(1000 * seed + D)
+    maxlen, overlap = 500, 200
+    stride = maxlen - overlap
+    src_rows, prot_src0, prot_nsrc, plens = [], [], [], []
+    for p in range(48):
+        prot_src0.append(len(src_rows))
+        Lp = int(rs.choice([rs.randint(3, 60), rs.randint(60, 500), rs.randint(501, 2600)]))
+        if Lp <= maxlen or rs.rand() < 0.25:
+            src_rows.append(Lp)                       # one source (also long proteins stitched beforehand)
+        else:
+            start = 0
+            while True:
+                rows = min(maxlen, Lp - start)
+                if start > 0 and rows <= overlap:
+                    break
+                src_rows.append(rows)
+                if start + rows >= Lp:
+                    break
+                start += stride
+        prot_nsrc.append(len(src_rows) - prot_src0[-1])
+        plens.append(src_rows[-1] if prot_nsrc[-1] == 1 else (prot_nsrc[-1] - 1) * stride + src_rows[-1])
+    dom_prot, seg_off, sb, se = [], [0], [], []
+    for p, Lp in enumerate(plens):
+        mode = rs.randint(0, 4)
+        doms = []
+        if mode == 0 and Lp >= 12:                    # a partition + the global domain (fusion candidate)
+            cuts = sorted(rs.choice(np.arange(3, Lp - 3), size=min(rs.randint(1, 6), max(1, (Lp - 6) // 4)), replace=False))
+            edges = [0] + [int(c) for c in cuts] + [Lp]
+            doms = [[(a, b)] for a, b in zip(edges[:-1], edges[1:]) if b - a >= 3]
+            if rs.rand() < 0.5 and len(doms) > 1:
+                doms.pop(rs.randint(len(doms)))       # rows no domain covers
+            doms.append([(0, Lp)])
+        else:                                         # arbitrary, possibly overlapping, multi-segment domains
+            for _ in range(rs.randint(1, 5)):
+                segs, rows = [], 0
+                for _ in range(rs.randint(1, 4)):
+                    a = rs.randint(0, Lp)
+                    b = rs.randint(a + 1, Lp + 1)
+                    segs.append((a, b))
+                    rows += b - a
+                if rows >= 3:
+                    doms.append(segs)
+            if not doms:
+                doms.append([(0, Lp)])
+        for segs in doms:
+            dom_prot.append(p)
+            for a, b in segs:
+                sb.append(a); se.append(b)
+            seg_off.append(len(sb))
+    total = int(sum(src_rows))
+    g = torch.Generator(device='cuda').manual_seed(seed)
+    layers = [torch.randn(total, D, generator=g, device='cuda') * (1 + l) + 3 * l for l in range(2)]
+    off = np.concatenate([[0], np.cumsum(src_rows)])
+    srcs = [[layers[l][off[i]:off[i + 1]] for i in range(len(src_rows))] for l in range(2)]
+    plan = make_plan(2, D, 3, 80, src_rows, prot_src0, prot_nsrc, dom_prot, seg_off, sb, se, maxlen=maxlen, overlap=overlap)
+    nd = len(dom_prot)
+    outs = {}
+    L = _lib.lib()
+    try:
+        for variant in (9, 0):
+            L.dctd_fp_set_variant(variant)
+            runs = []
+            for _ in range(3):
+                out = torch.full((nd, 480), 77, dtype=torch.int8, device='cuda')
+                execute_plan(plan, srcs, out)
+                runs.append(out.cpu().numpy())
+            assert all(np.array_equal(runs[0], r) for r in runs[1:]), f'variant {variant} is not reproducible'
+            outs[variant] = runs[0].astype(int)
+    finally:
+        L.dctd_fp_set_variant(0)
+    diff = np.abs(outs[0] - outs[9])
+    assert diff.max() <= 1, np.argwhere(diff > 1)[:5]
+    assert (diff != 0).mean() <= TOL_FRAC, (int((diff != 0).sum()), diff.size)
