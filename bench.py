@@ -199,7 +199,10 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
-        os.environ['NCCL_DEBUG'] = os.environ.get('DCTD_NCCL_DEBUG', 'WARN')    # stdout carries exactly one JSON line
+        # stdout carries exactly one JSON line: NCCL prints its version banner there at any NCCL_DEBUG level
+        os.environ.pop('NCCL_DEBUG', None)
+        if os.environ.get('DCTD_NCCL_DEBUG'):
+            os.environ['NCCL_DEBUG'] = os.environ['DCTD_NCCL_DEBUG']
         dist.init_process_group('nccl', device_id=dev)
 
     def barrier():

@@ -711,6 +711,9 @@ __global__ void __launch_bounds__(128) l1_merge_kernel(const MergeParams p) {
 // ------------------------------------------------------------------------------------------
 // pairwise scorer (dct-sim.py:12-50): one warp per protein pair
 // ------------------------------------------------------------------------------------------
+// VEC16: d is a multiple of 16 and the rows are 16-byte aligned -> lane c reads chunk c of both fingerprints as one
+// uint4 and takes four packed-byte SADs (bytes biased by 0x80 so that the unsigned SAD is |a - b| for int8)
+template <bool VEC16>
 __global__ void pair_scores_kernel(const int8_t *__restrict__ fps, int d, const long long *__restrict__ off,
                                    const int *__restrict__ pa, const int *__restrict__ pb, long long n_pairs,
                                    int *__restrict__ min_dist, int *__restrict__ last_dist) {
@@ -722,7 +725,21 @@ __global__ void pair_scores_kernel(const int8_t *__restrict__ fps, int d, const 
     for (long long i = a0; i < a1; ++i)
         for (long long j = b0; j < b1; ++j) {
             int s = 0;
-            for (int c = lane; c < d; c += 32) s += abs((int)fps[i * d + c] - (int)fps[j * d + c]);
+            if (VEC16) {
+                const uint4 *ra = reinterpret_cast<const uint4 *>(fps + i * d);
+                const uint4 *rb = reinterpret_cast<const uint4 *>(fps + j * d);
+                unsigned int acc = 0u;
+                for (int c = lane; c < (d >> 4); c += 32) {
+                    const uint4 x = ra[c], y = rb[c];
+                    acc = sad4(x.x ^ 0x80808080u, y.x ^ 0x80808080u, acc);
+                    acc = sad4(x.y ^ 0x80808080u, y.y ^ 0x80808080u, acc);
+                    acc = sad4(x.z ^ 0x80808080u, y.z ^ 0x80808080u, acc);
+                    acc = sad4(x.w ^ 0x80808080u, y.w ^ 0x80808080u, acc);
+                }
+                s = (int)acc;
+            } else {
+                for (int c = lane; c < d; c += 32) s += abs((int)fps[i * d + c] - (int)fps[j * d + c]);
+            }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
             best = min(best, s);
@@ -1118,8 +1135,13 @@ int dctd_l1_pair_scores(const int8_t *d_fps, int32_t d, const int64_t *d_off, co
     if (n_pairs == 0) return DCTD_OK;
     if (!d_fps || !d_off || !d_pair_a || !d_pair_b || !d_min_dist || !d_last_dist) return DCTD_ERR_ARG;
     const int warps = 4;
-    pair_scores_kernel<<<(unsigned)((n_pairs + warps - 1) / warps), warps * 32, 0, (cudaStream_t)stream>>>(
-        d_fps, d, (const long long *)d_off, d_pair_a, d_pair_b, n_pairs, d_min_dist, d_last_dist);
+    const unsigned grid = (unsigned)((n_pairs + warps - 1) / warps);
+    if (d % 16 == 0 && ((uintptr_t)d_fps & 15) == 0)
+        pair_scores_kernel<true><<<grid, warps * 32, 0, (cudaStream_t)stream>>>(
+            d_fps, d, (const long long *)d_off, d_pair_a, d_pair_b, n_pairs, d_min_dist, d_last_dist);
+    else
+        pair_scores_kernel<false><<<grid, warps * 32, 0, (cudaStream_t)stream>>>(
+            d_fps, d, (const long long *)d_off, d_pair_a, d_pair_b, n_pairs, d_min_dist, d_last_dist);
     DCTD_LAUNCH_CHECK();
     return DCTD_OK;
 }
