@@ -71,6 +71,7 @@ def lib():
         'dctd_fp_set_fusion': (C.c_int, [C.c_int]),
         'dctd_fp_timing_read': (C.c_int, [vp, vp, vp]),
         'dctd_fp_plan_dump': (C.c_int, [vp, vp, i64, vp, i64, C.POINTER(i64), C.POINTER(i64)]),
+        'dctd_fp_plan_dump_records': (C.c_int, [vp, vp, i64]),
         'dctd_scale_f64': (C.c_int, [vp, i64, vp, vp]),
         'dctd_idct_quant_f64': (C.c_int, [vp, i32, i32, i32, vp, vp]),
         'dctd_l1_packed_bytes': (sz, [i64, i32]),
@@ -82,7 +83,8 @@ def lib():
         'dctd_l1_topk_merge': (C.c_int, [vp, vp, i32, i64, i32, vp, vp, vp]),
         'dctd_l1_pair_scores': (C.c_int, [vp, i32, vp, vp, vp, i64, vp, vp, vp]),
     }
-    hooks = {'dctd_fp_set_variant', 'dctd_fp_set_fusion', 'dctd_fp_timing_read', 'dctd_fp_plan_dump', 'dctd_l1_set_mode'}
+    hooks = {'dctd_fp_set_variant', 'dctd_fp_set_fusion', 'dctd_fp_timing_read', 'dctd_fp_plan_dump', 'dctd_fp_plan_dump_records',
+             'dctd_l1_set_mode'}
     for name, (res, args) in sig.items():
         try:
             fn = getattr(L, name)      # AttributeError here = header / library mismatch

@@ -1272,6 +1272,14 @@ int dctd_fp_plan_dump(const dctd_fp_plan *plan, int32_t *pieces, int64_t max_pie
     return DCTD_OK;
 }
 
+/* test hook: copies the 32-word item records of the warp-specialised kernel (same order as the items) */
+int dctd_fp_plan_dump_records(const dctd_fp_plan *plan, int32_t *records, int64_t max_items) {
+    if (!plan || !records || max_items < 0) return DCTD_ERR_ARG;
+    const size_t n = std::min<size_t>((size_t)max_items, plan->items.size());
+    if (n) memcpy(records, plan->wsitems.data(), n * 32 * sizeof(int32_t));
+    return DCTD_OK;
+}
+
 int dctd_fp_execute(const dctd_fp_plan *plan, const void *const *h_src_ptrs, int64_t ld, int8_t *d_out,
                     int64_t out_stride, void *d_workspace, size_t workspace_bytes, uint32_t flags,
                     void *stream_) {

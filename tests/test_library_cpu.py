@@ -75,6 +75,62 @@ def test_planner_windows_and_split(lib):
     assert plan.workspace_bytes >= 3 * 2 * 640 * 8
 
 
+# word indices of the 128-byte item records of the warp-specialised kernel (csrc/fp_ws_kernel.cuh)
+W = {n: i for i, n in enumerate(
+    ['dom', 'layer', 'r0', 'r1', 'L', 'flags', 'split', 'nsplit', 'slab_base', 'counter', 'rider_dom', 'rider_slab',
+     'rider_nsplit', 'rider_slab_base', 'rider_counter', 'Lg', 'piv_src_a', 'piv_row_a', 'piv_src_b', 'piv_row_b', 'n_runs',
+     'piece_abs', 'run_src_a', 'run_row_a', 'run_src_b', 'run_row_b', 'run_rows', 'run_l0', 'run_g0'])}
+F_RIDER, F_PIVOT_INLINE, F_SPLIT = 1, 2, 4
+
+
+def _records(lib, plan, n_items):
+    rec = np.zeros((n_items, 32), dtype=np.int32)
+    assert lib.dctd_fp_plan_dump_records(plan.handle, rec.ctypes.data, n_items) == 0
+    return rec
+
+
+def test_planner_item_records_of_the_warp_specialised_kernel(lib):
+    # the fused protein of test_planner_single_source: domain 0 = rows 176..299 + 0..76, domain 1 = the whole protein
+    plan = _plan(lib, n_layers=2, D=1280, n=3, m=80, src_rows=[300], prot_src0=[0], prot_nsrc=[1],
+                 dom_prot=[0, 0], dom_seg_off=[0, 2, 3], seg_beg=[176, 0, 0], seg_end=[300, 77, 300])
+    _, items = _dump(lib, plan)
+    rec = _records(lib, plan, len(items))
+    assert (rec[:, [W['dom'], W['layer'], W['r0'], W['r1']]] == items[:, :4]).all()
+    for r in rec:
+        layer = r[W['layer']]
+        assert (r[W['piv_src_a']], r[W['piv_row_a']], r[W['piv_src_b']]) == (0, 0, -1)       # protein row 0
+        if r[W['dom']] == 0:      # the two-segment domain: carries the global fingerprint, streams two runs
+            assert r[W['flags']] == F_RIDER and r[W['n_runs']] == 2 and (r[W['L']], r[W['Lg']]) == (201, 300)
+            assert [r[W[k]] for k in ('run_src_a', 'run_row_a', 'run_src_b', 'run_rows', 'run_l0', 'run_g0')] == [0, 176, -1, 124, 0, 176]
+            assert r[W['rider_dom']] == 1 and r[W['rider_nsplit']] == 2
+            assert r[W['rider_slab_base']] == 2 * layer and r[W['rider_slab']] == 2 * layer + 1
+            assert r[W['rider_counter']] == 1 + layer                  # counter 0 is the work queue
+        else:                     # the global domain itself only streams the rows no other domain covers (77..175)
+            assert r[W['flags']] == F_SPLIT and r[W['n_runs']] == 1 and r[W['rider_dom']] == -1
+            assert [r[W[k]] for k in ('run_row_a', 'run_rows', 'run_l0', 'run_g0')] == [77, 99, 77, 77]
+            assert (r[W['split']], r[W['nsplit']], r[W['slab_base']], r[W['counter']]) == (0, 2, 2 * layer, 1 + layer)
+    # an unfused domain that starts at its own first row takes the pivot from its first stage
+    plan = _plan(lib, n_layers=1, D=640, n=3, m=80, src_rows=[500, 500, 500, 334], prot_src0=[0],
+                 prot_nsrc=[4], dom_prot=[0, 0], dom_seg_off=[0, 1, 2], seg_beg=[0, 320], seg_end=[250, 420])
+    _, items = _dump(lib, plan)
+    rec = _records(lib, plan, len(items))
+    by_dom = {int(r[W['dom']]): r for r in rec}
+    assert by_dom[0][W['flags']] == F_PIVOT_INLINE and by_dom[0][W['n_runs']] == 1
+    # rows 320..419 lie in the overlap of windows 0 and 1: a dual-source run whose first row is the (dual) pivot
+    d1 = by_dom[1]
+    assert d1[W['flags']] == F_PIVOT_INLINE and d1[W['n_runs']] == 1
+    assert [d1[W[k]] for k in ('run_src_a', 'run_row_a', 'run_src_b', 'run_row_b', 'run_rows')] == [0, 320, 1, 20, 100]
+    # a domain split over several items: every item but the first needs the pivot as a separate stage
+    plan = _plan(lib, n_layers=1, D=640, n=3, m=80, src_rows=[1500], prot_src0=[0], prot_nsrc=[1],
+                 dom_prot=[0], dom_seg_off=[0, 1], seg_beg=[0], seg_end=[1500])
+    _, items = _dump(lib, plan)
+    rec = _records(lib, plan, len(items))
+    assert len(rec) == 3 and (rec[:, W['nsplit']] == 3).all() and sorted(rec[:, W['split']]) == [0, 1, 2]
+    for r in rec:
+        assert r[W['flags']] == (F_SPLIT | (F_PIVOT_INLINE if r[W['r0']] == 0 else 0))
+        assert (r[W['piv_src_a']], r[W['piv_row_a']]) == (0, 0) and r[W['run_row_a']] == r[W['r0']]
+
+
 def test_planner_rejects_bad_input(lib):
     with pytest.raises(ValueError):      # domain shorter than n: the reference's reshape fails too
         _plan(lib, n_layers=1, D=640, n=3, m=80, src_rows=[10], prot_src0=[0], prot_nsrc=[1],
