@@ -152,6 +152,8 @@ struct ScanParams {
     int d, k;
     long long n_groups;         // groups visited (virtual index v; real group = v * gstride)
     long long gstride;          // 1 = every group, s = every s-th group (threshold sample)
+    long long skip;             // s > 1: visit every group EXCEPT every s-th one (the sample was scored already);
+                                // virtual index v -> real group v + v / (s - 1) + 1.  0 = off
     long long groups_per_split;
     const int *qflags;          // optional [nq]: only query tiles with a flagged query are processed
     // heap mode (l1_scan_kernel)
@@ -163,6 +165,11 @@ struct ScanParams {
     int *cnt;                   // [nq] candidates appended (may exceed cmax: overflow)
     int cmax;
 };
+
+// real group of virtual group v (see ScanParams::gstride / skip)
+__device__ __forceinline__ long long real_group(const ScanParams &p, long long v) {
+    return p.skip ? v + v / (p.skip - 1) + 1 : v * p.gstride;
+}
 
 template <int NW, int TQ>
 __device__ __forceinline__ void load_queries(const ScanParams &p, unsigned char *qs, long long q0, int dpad) {
@@ -187,11 +194,12 @@ __device__ __forceinline__ void producer_loop(const ScanParams &p, unsigned long
         const int ng = (int)min((long long)kTD, g_end - v);
         const unsigned int gbytes = 32u * (unsigned int)dpad;
         mbar_expect_tx(&full[s], (unsigned int)ng * gbytes);
-        if (p.gstride == 1) {
-            bulk_g2s(st + (size_t)s * tile_bytes, p.packed + v * C * 32, (unsigned int)ng * gbytes, &full[s]);
+        const long long g0 = real_group(p, v);
+        if (real_group(p, v + ng - 1) == g0 + ng - 1) {      // the tile's groups are adjacent: one copy
+            bulk_g2s(st + (size_t)s * tile_bytes, p.packed + g0 * C * 32, (unsigned int)ng * gbytes, &full[s]);
         } else {
             for (int b = 0; b < ng; ++b)
-                bulk_g2s(st + (size_t)s * tile_bytes + (size_t)b * gbytes, p.packed + (v + b) * p.gstride * C * 32,
+                bulk_g2s(st + (size_t)s * tile_bytes + (size_t)b * gbytes, p.packed + real_group(p, v + b) * C * 32,
                          gbytes, &full[s]);
         }
     }
@@ -309,7 +317,7 @@ __global__ void __launch_bounds__((kWarps + 1) * 32, 1) l1_scan_kernel(const Sca
         for (int a = 0; a < TQ; ++a) {
 #pragma unroll
             for (int b = 0; b < kTD; ++b) {
-                const long long id = (vbase + b) * p.gstride * 32 + lane;
+                const long long id = real_group(p, vbase + b) * 32 + lane;
                 const bool valid = (vbase + b) < g_end && id < p.n;
                 const unsigned long long key = ((unsigned long long)acc[a][b] << kIdBits) | (unsigned long long)id;
                 const bool pass = valid && key < wthr[a];
@@ -450,6 +458,29 @@ __global__ void __launch_bounds__(256) l1_kth_kernel(const unsigned int *mins, i
 }
 
 // ------------------------------------------------------------------------------------------
+// The sample's exact top-k (sorted keys, kKeyMax padding) become the first candidates of every query, so the
+// threshold scan can leave the sampled groups out: a sampled vector beyond its sample's k-th key cannot be among
+// the k best overall.  One warp per query; also sets the candidate counter (no memset).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) l1_seed_kernel(const unsigned long long *thr_keys, long long nq, int k,
+                                                      unsigned long long *cand, int *cnt, int cmax) {
+    const int lane = threadIdx.x & 31;
+    const long long qi = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (qi >= nq) return;
+    int valid = 0;
+    for (int i = lane; i < k; i += 32) {
+        const unsigned long long key = thr_keys[qi * k + i];
+        if (key != kKeyMax) {            // keys are sorted: the valid ones are a prefix
+            cand[qi * cmax + i] = key;
+            ++valid;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) valid += __shfl_xor_sync(0xffffffffu, valid, o);
+    if (lane == 0) cnt[qi] = valid;
+}
+
+// ------------------------------------------------------------------------------------------
 // threshold scan: every vector whose distance is <= the query's threshold (k-th best of a sample of
 // the database, an upper bound of the true k-th best) is appended to the query's candidate list in
 // global memory.  No per-warp selection state: the scan is SADs + one compare per pair.
@@ -503,6 +534,11 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) l1_thresh_scan_kernel(const 
         if (qi < p.nq) th = p.thr_keys[qi * p.k + p.k - 1];
         tdist[a] = (qi < p.nq) ? ((th == kKeyMax) ? 0xffffffffu : (unsigned int)(th >> kIdBits)) : 0u;
     }
+    // real group of the tile's first virtual group, kept up without a division per tile: with `skip`, virtual group
+    // v = vq * (skip - 1) + vr is real group v + vq + 1
+    const long long sk1 = p.skip ? p.skip - 1 : 1;
+    long long vq = p.skip ? g_begin / sk1 : 0;
+    int vr = p.skip ? (int)(g_begin % sk1) : 0;
     for (int t = 0; t < n_tiles; ++t) {
         const int s = t % STAGES;
         mbar_wait(&full[s], (unsigned int)((t / STAGES) & 1));
@@ -510,19 +546,25 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) l1_thresh_scan_kernel(const 
         sad_tile<TQ, kTD>(reinterpret_cast<const uint4 *>(st + (size_t)s * tile_bytes), qs4, C, lane, acc);
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[s]);
+        const long long vbase = g_begin + (long long)t * kTD;
+        long long greal[kTD];
+#pragma unroll
+        for (int b = 0; b < kTD; ++b)
+            greal[b] = p.skip ? (vbase + b) + vq + ((vr + b >= sk1) ? 1 : 0) + 1 : (vbase + b) * p.gstride;
+        vr += kTD;
+        if (p.skip && vr >= sk1) { vr -= (int)sk1; ++vq; }
         bool hit = false;
 #pragma unroll
         for (int a = 0; a < TQ; ++a)
 #pragma unroll
             for (int b = 0; b < kTD; ++b) hit = hit || (acc[a][b] <= tdist[a]);
         if (!__any_sync(0xffffffffu, hit)) continue;
-        const long long vbase = g_begin + (long long)t * kTD;
 #pragma unroll
         for (int a = 0; a < TQ; ++a) {
             const long long qi = q0 + warp * TQ + a;
 #pragma unroll
             for (int b = 0; b < kTD; ++b) {
-                const long long id = (vbase + b) * 32 + lane;
+                const long long id = greal[b] * 32 + lane;
                 const bool pass = (vbase + b) < g_end && id < p.n && qi < p.nq && acc[a][b] <= tdist[a];
                 append_candidates(p, qi, pass, ((unsigned long long)acc[a][b] << kIdBits) | (unsigned long long)id, lane);
             }
@@ -754,6 +796,8 @@ __global__ void pair_scores_kernel(const int8_t *__restrict__ fps, int d, const 
 // ------------------------------------------------------------------------------------------
 // host-side configuration shared by workspace_bytes and topk
 // ------------------------------------------------------------------------------------------
+int g_l1_mode = 0;   // tuning / test hook (dctd_l1_set_mode): 0 = automatic, 1 = force the heap scan, 2 = heap-scan
+                     // thresholds in the streaming regime, 3 = the threshold scan revisits the sampled groups
 constexpr long long kSMs = 148;
 constexpr size_t kSmemLimit = 227 * 1024;
 
@@ -860,7 +904,8 @@ bool make_plan(long long nq, long long n, int d, int k, TopkPlan *pl) {
             const size_t qt = (size_t)tc.nw * tc.tq;
             tc.smem = 128 + qt * dpad + (size_t)kStagesMax * kTDmax * 32 * dpad + 64;
             tc.n_qtiles = (nq + (long long)qt - 1) / (long long)qt;
-            pick_splits(n_groups, kTDmax, tc.n_qtiles, 2, &tc.splits, &tc.groups_per_split);
+            // the sampled groups are not scanned again (their top-k seeds the candidate lists)
+            pick_splits(g_l1_mode == 3 ? n_groups : n_groups - sg, kTDmax, tc.n_qtiles, 2, &tc.splits, &tc.groups_per_split);
         }
         if (tc.smem <= kSmemLimit && make_config(nq, sg, d, k, &pl->samp)) {
             pl->tc = tc;
@@ -960,8 +1005,6 @@ int run_merge(const unsigned long long *keys, long long parts, long long nq, int
     DCTD_LAUNCH_CHECK();
     return DCTD_OK;
 }
-
-int g_l1_mode = 0;   // tuning / test hook: 0 = automatic, 1 = force the heap scan, 2 = heap-scan thresholds in the streaming regime
 
 }  // namespace
 
@@ -1063,12 +1106,23 @@ int dctd_l1_topk(const int8_t *d_q, int64_t nq, const void *d_packed, int64_t n,
         if (rc != DCTD_OK) return rc;
     }
     // 2. one pass over the database: append everything within the threshold
-    if (!(pl.tc.stream && g_l1_mode != 2)) DCTD_CUDA_TRY(cudaMemsetAsync(cnt, 0, (size_t)nq * sizeof(int), stream));
+    if (pl.tc.stream) {
+        if (g_l1_mode == 2) DCTD_CUDA_TRY(cudaMemsetAsync(cnt, 0, (size_t)nq * sizeof(int), stream));
+    } else if (g_l1_mode == 3) {
+        DCTD_CUDA_TRY(cudaMemsetAsync(cnt, 0, (size_t)nq * sizeof(int), stream));
+    } else {
+        l1_seed_kernel<<<(unsigned)((nq + 3) / 4), 128, 0, stream>>>(thr, nq, k, cand, cnt, pl.cmax);
+        DCTD_LAUNCH_CHECK();
+    }
     {
         ScanParams s2 = sp;
         s2.thr_keys = thr; s2.cand = cand; s2.cnt = cnt; s2.cmax = pl.cmax;
         s2.n_groups = (n + 31) / 32;
         const ThreshConfig &tc = pl.tc;
+        if (!tc.stream && g_l1_mode != 3) {       // every group but the sampled ones (mode 3: rescan them, for A/B runs)
+            s2.skip = pl.gstride;
+            s2.n_groups -= (s2.n_groups + pl.gstride - 1) / pl.gstride;
+        }
         if (tc.stream) {
             ScanFn fn = tc.tq == 4 ? l1_thresh_stream_kernel<4> : (tc.tq == 8 ? l1_thresh_stream_kernel<8> : l1_thresh_stream_kernel<16>);
             int per_sm = 0;
