@@ -553,20 +553,26 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) l1_thresh_scan_kernel(const 
             greal[b] = p.skip ? (vbase + b) + vq + ((vr + b >= sk1) ? 1 : 0) + 1 : (vbase + b) * p.gstride;
         vr += kTD;
         if (p.skip && vr >= sk1) { vr -= (int)sk1; ++vq; }
-        bool hit = false;
+        // one bit per (query, group) pair with a lane within the threshold, OR-ed over the warp in one REDUX: the
+        // compares and this reduction are all the selection work of a tile unless something passes, and then only the
+        // pairs that do pass are visited (these instructions share the ALU pipe with the SADs)
+        unsigned int mask = 0u;
 #pragma unroll
         for (int a = 0; a < TQ; ++a)
 #pragma unroll
-            for (int b = 0; b < kTD; ++b) hit = hit || (acc[a][b] <= tdist[a]);
-        if (!__any_sync(0xffffffffu, hit)) continue;
+            for (int b = 0; b < kTD; ++b) mask |= (acc[a][b] <= tdist[a]) ? (1u << (a * kTD + b)) : 0u;
+        const unsigned int any = __reduce_or_sync(0xffffffffu, mask);
+        if (!any) continue;
 #pragma unroll
         for (int a = 0; a < TQ; ++a) {
-            const long long qi = q0 + warp * TQ + a;
 #pragma unroll
             for (int b = 0; b < kTD; ++b) {
-                const long long id = greal[b] * 32 + lane;
-                const bool pass = (vbase + b) < g_end && id < p.n && qi < p.nq && acc[a][b] <= tdist[a];
-                append_candidates(p, qi, pass, ((unsigned long long)acc[a][b] << kIdBits) | (unsigned long long)id, lane);
+                if (any & (1u << (a * kTD + b))) {          // warp-uniform
+                    const long long qi = q0 + warp * TQ + a;
+                    const long long id = greal[b] * 32 + lane;
+                    const bool pass = (vbase + b) < g_end && id < p.n && qi < p.nq && acc[a][b] <= tdist[a];
+                    append_candidates(p, qi, pass, ((unsigned long long)acc[a][b] << kIdBits) | (unsigned long long)id, lane);
+                }
             }
         }
     }
