@@ -206,14 +206,18 @@ __device__ __forceinline__ void producer_loop(const ScanParams &p, unsigned long
 }
 
 // distances of this warp's TQ queries against lane's vector of each of the kTD groups of one stage
-template <int TQ, int kTD>
-__device__ __forceinline__ void sad_tile(const uint4 *st4, const uint4 *qs4, int C, int lane,
+// CT: compile-time chunk count (d = 16 CT; 30 for the reference's 480-byte fingerprints) - the chunk loop is then fully
+// unrolled and every shared-memory address is base + immediate: the address increments of the rolled loop run on the
+// same ALU pipe as the SADs (5 % of its slots).  CT = 0: runtime C.
+template <int TQ, int kTD, int CT = 0>
+__device__ __forceinline__ void sad_tile(const uint4 *st4, const uint4 *qs4, int C_, int lane,
                                          unsigned int (&acc)[TQ][kTD]) {
+    const int C = CT ? CT : C_;
 #pragma unroll
     for (int a = 0; a < TQ; ++a)
 #pragma unroll
         for (int b = 0; b < kTD; ++b) acc[a][b] = 0u;
-#pragma unroll 2
+#pragma unroll(CT ? CT : 2)
     for (int c = 0; c < C; ++c) {
         uint4 dv[kTD], qv[TQ];
 #pragma unroll
@@ -496,7 +500,7 @@ __device__ __forceinline__ void append_candidates(const ScanParams &p, long long
     if (pass && slot < p.cmax) p.cand[qi * p.cmax + slot] = key;
 }
 
-template <int NW, int TQ, int kTD, int STAGES>
+template <int NW, int TQ, int kTD, int STAGES, int CT = 0>
 __global__ void __launch_bounds__((NW + 1) * 32, 1) l1_thresh_scan_kernel(const ScanParams p) {
     constexpr int QT = NW * TQ;
     extern __shared__ __align__(128) unsigned char smem[];
@@ -543,7 +547,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) l1_thresh_scan_kernel(const 
         const int s = t % STAGES;
         mbar_wait(&full[s], (unsigned int)((t / STAGES) & 1));
         unsigned int acc[TQ][kTD];
-        sad_tile<TQ, kTD>(reinterpret_cast<const uint4 *>(st + (size_t)s * tile_bytes), qs4, C, lane, acc);
+        sad_tile<TQ, kTD, CT>(reinterpret_cast<const uint4 *>(st + (size_t)s * tile_bytes), qs4, C, lane, acc);
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[s]);
         const long long vbase = g_begin + (long long)t * kTD;
@@ -1140,7 +1144,8 @@ int dctd_l1_topk(const int8_t *d_q, int64_t nq, const void *d_packed, int64_t n,
         } else {
             s2.groups_per_split = tc.groups_per_split;
             ScanFn fn;
-            if (tc.nw == 16) fn = l1_thresh_scan_kernel<16, 8, kTDmax, kStagesMax>;
+            if (tc.nw == 16 && d == 480 && g_l1_mode != 5) fn = l1_thresh_scan_kernel<16, 8, kTDmax, kStagesMax, 30>;
+            else if (tc.nw == 16) fn = l1_thresh_scan_kernel<16, 8, kTDmax, kStagesMax>;
             else if (tc.tq == 8) fn = l1_thresh_scan_kernel<8, 8, kTDmax, kStagesMax>;
             else fn = l1_thresh_scan_kernel<8, 4, kTDmax, kStagesMax>;
             if (tc.n_qtiles > 65535) return DCTD_ERR_UNSUPPORTED;

@@ -40,7 +40,7 @@ def main():
             e1.record()
             torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / iters
-            out[{0: 'thresh', 1: 'heap', 2: 'thresh_heap_sample', 3: 'thresh_rescan_sample'}.get(mode, f'mode{mode}')] = dict(ms=ms, pairs_per_s=nq * n / ms * 1e3, db_GBps=n * 480 / ms / 1e6)
+            out[{0: 'thresh', 1: 'heap', 2: 'thresh_heap_sample', 3: 'thresh_rescan_sample', 5: 'thresh_rolled_chunk_loop'}.get(mode, f'mode{mode}')] = dict(ms=ms, pairs_per_s=nq * n / ms * 1e3, db_GBps=n * 480 / ms / 1e6)
             out['same'] = bool(out.get('same', True) and (('ref' not in out) or (torch.equal(out['ref'][0], r[0]) and torch.equal(out['ref'][1], r[1]))))
             out.setdefault('ref', r)
         out.pop('ref')
