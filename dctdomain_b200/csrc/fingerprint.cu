@@ -75,8 +75,8 @@ struct Layout {             // thread / shared-memory layout derived from (D, n,
 
 struct WsLayout {           // shared-memory layout of the warp-specialised kernel (fp_ws_kernel.cuh)
     int nst;                // TMA ring stages
-    int DS;                 // pass-2a splits of the column range
-    int H;                  // pass-2a coefficient pairing: a thread owns k and k + H (H even)
+    int DSo, DSe;           // pass-2a splits of the folded column range for odd / even coefficient pairs
+    int H;                  // pass-2a coefficient pairing: a thread owns k and k + H (H = 0 mod 4)
     unsigned off_bars, off_meta, off_basis, off_desc, off_ring, off_u, off_ye, off_yo, off_f, off_tt, off_tm, off_mj;
     unsigned smem;
 };
@@ -838,13 +838,13 @@ WsLayout make_ws_layout(int m, int max_smem) {
     using Cfg = WsCfg<K, DC, RIDER>;
     WsLayout w{};
     const int N = K + 1, nk = m - 1;
-    // pass 2a: a thread owns the coefficient pair (k, k + H); the columns are split over DS thread groups in whole
-    // octets of float4 steps.  DS = as many groups as the finisher threads allow, then lowered as long as the longest
-    // split does not grow (fewer partial sums to add up).
-    w.H = ((nk + 1) / 2 + 1) / 2 * 2;
-    const int OQ = std::max(1, DC / 64);
-    w.DS = std::max(1, std::min(kWsFinThreads / w.H, OQ));
-    while (w.DS > 1 && (OQ + w.DS - 2) / (w.DS - 1) == (OQ + w.DS - 1) / w.DS) --w.DS;
+    // pass 2a: a thread owns the coefficient pair (k, k + H), H = 0 (mod 4) so that both are of one class mod 4; the
+    // D/4 folded columns are split over DSe thread groups for the even pairs and twice as many for the odd ones (an odd
+    // pair costs twice as much per column): (H/2) * (DSo + DSe) units for the 256 finisher threads
+    w.H = ((nk + 1) / 2 + 3) / 4 * 4;
+    const int QQ = std::max(1, DC / 16);
+    w.DSe = std::max(1, std::min(kWsFinThreads / (3 * (w.H / 2)), QQ / 2));
+    w.DSo = std::min(2 * w.DSe, QQ);
     size_t off = 0;
     auto take = [&](size_t bytes) { const size_t o = off; off += dctd::align_up(bytes, 128); return (unsigned)o; };
     w.off_bars = take((2 * kWsMaxStages + 4) * sizeof(unsigned long long));
@@ -854,7 +854,7 @@ WsLayout make_ws_layout(int m, int max_smem) {
     w.off_u = take((size_t)2 * K * DC * sizeof(double));
     w.off_ye = take((size_t)N * (DC / 2) * sizeof(float));
     w.off_yo = take((size_t)N * (DC / 2) * sizeof(float));
-    w.off_f = take(((size_t)w.DS * N * nk + (size_t)N * nk + (size_t)N * m) * sizeof(double));
+    w.off_f = take(((size_t)(w.DSo + w.DSe) * N * w.H + (size_t)N * nk + (size_t)N * m) * sizeof(double));
     w.off_tt = take((size_t)(4 * DC + 8 * m) * sizeof(float));
     w.off_tm = take((size_t)4 * m * sizeof(double));
     w.off_mj = take((size_t)N * K * sizeof(double));

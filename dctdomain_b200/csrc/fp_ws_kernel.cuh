@@ -57,7 +57,7 @@ struct WsCfg {
     static constexpr int T = 32 * (1 + NCW + kWsFinWarps);
     static constexpr int STAGE_BYTES = R * DC * 4;
     static constexpr int FLUSH_EVERY = (8 / R) < 1 ? 1 : (8 / R);
-    static_assert(DC % 128 == 0, "one consumer warp per 128 columns");
+    static_assert(DC % 128 == 0, "one consumer warp per 128 columns (and float4 steps over D/4 columns)");
     static_assert(R % 2 == 0, "dual stages hold R/2 rows of each window");
 };
 
@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(WsCfg<K, DC, RIDER>::T, 1) fp_ws_kernel(const 
     using Cfg = WsCfg<K, DC, RIDER>;
     using namespace dctd::tma;
     constexpr int N = K + 1, KS = Cfg::KS, R = Cfg::R, NCW = Cfg::NCW, NFT = kWsFinThreads;
-    constexpr int D = DC, half = DC / 2, HQ = DC / 8;
+    constexpr int D = DC, half = DC / 2, quarter = DC / 4;
     extern __shared__ __align__(16) unsigned char smem[];
     const WsLayout wl = p.wl;
     const int NST = wl.nst;
@@ -117,10 +117,10 @@ __global__ void __launch_bounds__(WsCfg<K, DC, RIDER>::T, 1) fp_ws_kernel(const 
     int *desc = reinterpret_cast<int *>(smem + wl.off_desc);               // [kWsDescSlots][32]
     unsigned char *ring = smem + wl.off_ring;                              // [NST][STAGE_BYTES]
     double *ubuf = reinterpret_cast<double *>(smem + wl.off_u);            // [2][K][D]
-    float *Ye = reinterpret_cast<float *>(smem + wl.off_ye);               // [N][D/2]  y'[d] + y'[D-1-d]
-    float *Yo = reinterpret_cast<float *>(smem + wl.off_yo);               // [N][D/2]  y'[d] - y'[D-1-d]
-    double *Fs = reinterpret_cast<double *>(smem + wl.off_f);              // Fp [DS][N][nk] | Fr [N][nk] | Z [N][m]
-    float *TT = reinterpret_cast<float *>(smem + wl.off_tt);               // cos(pi (i mod 4D) / 2D), i < 4D + 8m
+    float *Ye = reinterpret_cast<float *>(smem + wl.off_ye);               // [2][N][D/4]  EE | EO (see stage1)
+    float *Yo = reinterpret_cast<float *>(smem + wl.off_yo);               // [2][N][D/4]  OD | OR
+    double *Fs = reinterpret_cast<double *>(smem + wl.off_f);              // pass-2a partial sums | Fr [N][nk] | Z [N][m]
+    float *TT = reinterpret_cast<float *>(smem + wl.off_tt);               // [even i | odd i] halves of cos(pi (i mod 4D) / 2D), i < 4D + 8m
     double *Tm = reinterpret_cast<double *>(smem + wl.off_tm);             // cos(pi i / 2m), i < 4m
     double *Mj = reinterpret_cast<double *>(smem + wl.off_mj);             // [N][K] cos(pi (2j+1) k / 2n)
     __shared__ int u_slot[2];
@@ -134,7 +134,9 @@ __global__ void __launch_bounds__(WsCfg<K, DC, RIDER>::T, 1) fp_ws_kernel(const 
         for (int b = 0; b < 2; ++b) { mbar_init(&u_full[b], NCW); mbar_init(&u_empty[b], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int i = tid; i < 4 * D + 8 * m; i += blockDim.x) TT[i] = __ldg(p.table + i);
+    // cos(pi i / 2D) split by the parity of i: odd k only ever look up odd i = (2d+1) k, even k even i, and inside
+    // one parity class lanes with consecutive k are an odd number of entries apart (conflict-free)
+    for (int i = tid; i < 4 * D + 8 * m; i += blockDim.x) TT[(i & 1) * (2 * D + 4 * m) + (i >> 1)] = __ldg(p.table + i);
     for (int i = tid; i < 4 * m; i += blockDim.x) Tm[i] = cospi((double)i / (2.0 * m));
     for (int i = tid; i < N * K; i += blockDim.x) {
         const int j = i / K, k = i % K + 1;
@@ -432,10 +434,12 @@ __global__ void __launch_bounds__(WsCfg<K, DC, RIDER>::T, 1) fp_ws_kernel(const 
         // =============================== finishers ===============================
         const int ftid = tid - 32 * (1 + NCW);
         const int fwarp = ftid >> 5;
-        const int DS = wl.DS, H = wl.H;
-        const unsigned int tt_u32 = smem_u32(TT), tt_end = tt_u32 + 16u * D;
-        double *Fp = Fs;                                   // [DS][N][nk]
-        double *Fr = Fs + (size_t)DS * N * nk;             // [N][nk]
+        const int DSo = wl.DSo, DSe = wl.DSe, H = wl.H, HP = wl.H / 2;
+        const int TH = 2 * D + 4 * m;                      // entries of one parity half of the cosine table
+        constexpr int QQ = quarter / 4;                    // float4 steps over d < D/4
+        const unsigned int tt_u32 = smem_u32(TT);
+        double *Fp = Fs;                                   // odd k [DSo][N][H] | even k [DSe][N][H]
+        double *Fr = Fs + (size_t)(DSo + DSe) * N * H;     // [N][nk]
         double *Z = Fr + (size_t)N * nk;                   // [N][m]
         auto fin_bar = [&]() { named_bar_sync(1, NFT); };
 
@@ -460,20 +464,31 @@ __global__ void __launch_bounds__(WsCfg<K, DC, RIDER>::T, 1) fp_ws_kernel(const 
 #pragma unroll
             for (int j = 0; j < N; ++j) yo[j] = (float)((y[j] - mn) * inv - 0.5);
         };
-        // Ye / Yo from the u sums; cos(pi (2(D-1-d)+1) k / 2D) = (-1)^k cos(pi (2d+1) k / 2D), so even k only
-        // need e[d] = y'[d] + y'[D-1-d] and odd k only o[d] = y'[d] - y'[D-1-d], d < D/2
+        // Folded inputs of pass 2a from the u sums.  With x = pi (2d+1) k / 2D:
+        //   cos at column D-1-d   = (-1)^k cos x                      -> e[d] = y'[d] + y'[D-1-d] (even k), o[d] = y'[d] - y'[D-1-d] (odd k), d < D/2
+        //   cos at column D/2-1-d = cos(k pi/2 - x) = +cos x, sin x, -cos x, -sin x for k = 0, 1, 2, 3 (mod 4)
+        //                                                              -> EE = e[d] + e[D/2-1-d] (k = 0 mod 4), EO = e[d] - e[D/2-1-d] (k = 2 mod 4),
+        //                                                                 OD = o[d] with cos x and OR = o[D/2-1-d] with +-sin x (odd k), d < D/4
+        // Ye = [EE | EO], Yo = [OD | OR], each [N][D/4]: even k need half the products of the one-fold form.
         auto stage1 = [&](auto getu) {
-            for (int d = ftid; d < half; d += NFT) {
-                double ua[K], ub2[K];
+            for (int d = ftid; d < quarter; d += NFT) {
+                const int c[4] = {d, half - 1 - d, half + d, D - 1 - d};
+                float y[4][N];
 #pragma unroll
-                for (int k = 0; k < K; ++k) { ua[k] = getu(k, d); ub2[k] = getu(k, D - 1 - d); }
-                float ya[N], yb[N];
-                column(ua, ya);
-                column(ub2, yb);
+                for (int i = 0; i < 4; ++i) {
+                    double u[K];
+#pragma unroll
+                    for (int k = 0; k < K; ++k) u[k] = getu(k, c[i]);
+                    column(u, y[i]);
+                }
 #pragma unroll
                 for (int j = 0; j < N; ++j) {
-                    Ye[j * half + d] = ya[j] + yb[j];
-                    Yo[j * half + d] = ya[j] - yb[j];
+                    const float e0 = y[0][j] + y[3][j], o0 = y[0][j] - y[3][j];      // columns d, D-1-d
+                    const float e1 = y[1][j] + y[2][j], o1 = y[1][j] - y[2][j];      // columns D/2-1-d, D/2+d
+                    Ye[j * quarter + d] = e0 + e1;
+                    Ye[(N + j) * quarter + d] = e0 - e1;
+                    Yo[j * quarter + d] = o0;
+                    Yo[(N + j) * quarter + d] = o1;
                 }
             }
         };
@@ -483,25 +498,26 @@ __global__ void __launch_bounds__(WsCfg<K, DC, RIDER>::T, 1) fp_ws_kernel(const 
         WS_T0();
         auto finish_rest = [&](int dom_index, int layer) {
             WS_ACC(t_s1);
-            // ---- pass 2a: F[j][k] = sum_{d < D/2} (e|o)[j][d] cos(pi (2d+1) k / 2D).  Cosines from the shared table
-            //      TT[i] = cos(pi (i mod 4D) / 2D) at i = (2d+1) k (lanes hold consecutive k, the stride 2d+1 is odd:
-            //      conflict-free), four columns per step at i + {0, 2k, 4k, 6k} (the table is extended by 8m entries, so
-            //      only i itself wraps); e / o are broadcast 16-byte loads.  A thread owns two coefficients of the same
-            //      parity, k and k + H (H even), so that one load of e / o feeds both: the shared-memory pipe, which
-            //      also carries the TMA writes and the consumers' reads, is what bounds this pass ----
-            for (int w = ftid; w < H * DS; w += NFT) {
-                const int ds = w / H, ka = 1 + w % H;
+            // ---- pass 2a: F[j][k] = sum_d y'[j][d] cos(pi (2d+1) k / 2D) on the folded inputs, d < D/4.  A thread owns
+            //      two coefficients of one class mod 4, k and k + H (H = 0 mod 4), so one broadcast load of the inputs
+            //      feeds both; lanes hold consecutive k of one parity; cosines come from the parity-split shared table at
+            //      byte addresses (entry ((2d+1) k - parity) / 2, four columns per step at +k entries each; the table is
+            //      extended by 4m entries so only the first address wraps).  Odd k also need sin x = cos(x -+ pi/2): the
+            //      same table half, D/2 entries back (k = 1 mod 4) or ahead (k = 3 mod 4, which supplies the minus sign).
+            //      An odd pair costs twice an even one per column, so the odd pairs split the columns twice as finely. ----
+            for (int w = ftid; w < HP * (DSo + DSe); w += NFT) {
+                const bool odd = w < HP * DSo;
+                const int wi = odd ? w : w - HP * DSo;
+                const int DSx = odd ? DSo : DSe;
+                const int ds = wi / HP, ka = 2 * (wi % HP) + (odd ? 1 : 2);
                 if (ka > nk) continue;
                 const bool hasb = ka + H <= nk;
                 const int kb = hasb ? ka + H : ka;
-                // split boundaries in multiples of 8 quads (32 columns) when the width allows: no remainder loop
-                const int q0 = (HQ % 8 == 0) ? (HQ / 8 * ds / DS) * 8 : HQ * ds / DS;
-                const int q1 = (HQ % 8 == 0) ? (HQ / 8 * (ds + 1) / DS) * 8 : HQ * (ds + 1) / DS;
-                const float *yb = ((ka & 1) ? Yo : Ye) + 4 * q0;
-                // table positions as shared-memory byte addresses: one add per lookup, no index scaling
-                unsigned int oa = tt_u32 + 4u * (unsigned int)(((long long)(8 * q0 + 1) * ka) % (4LL * D));
-                unsigned int ob = tt_u32 + 4u * (unsigned int)(((long long)(8 * q0 + 1) * kb) % (4LL * D));
-                const unsigned int sa = 8u * ka, sb = 8u * kb;      // 2k entries in bytes
+                const int q0 = QQ * ds / DSx, q1 = QQ * (ds + 1) / DSx;
+                const unsigned int tbase = tt_u32 + (odd ? 4u * (unsigned int)TH : 0u), tend = tbase + 8u * D;
+                unsigned int oa = tbase + 4u * (unsigned int)((((long long)(8 * q0 + 1) * ka - (odd ? 1 : 0)) / 2) % (2LL * D));
+                unsigned int ob = tbase + 4u * (unsigned int)((((long long)(8 * q0 + 1) * kb - (odd ? 1 : 0)) / 2) % (2LL * D));
+                const unsigned int sa = 4u * ka, sb = 4u * kb;          // k entries in bytes
                 double fa[N], fb[N];
 #pragma unroll
                 for (int j = 0; j < N; ++j) { fa[j] = 0.0; fb[j] = 0.0; }
@@ -509,24 +525,6 @@ __global__ void __launch_bounds__(WsCfg<K, DC, RIDER>::T, 1) fp_ws_kernel(const 
                 pk2 aa[N][2], ab[N][2];
 #pragma unroll
                 for (int j = 0; j < N; ++j) { aa[j][0] = zero; aa[j][1] = zero; ab[j][0] = zero; ab[j][1] = zero; }
-                auto quad = [&]() {
-                    const pk2 ca01 = pk(lds_f32(oa), lds_f32(oa + sa)), ca23 = pk(lds_f32(oa + 2 * sa), lds_f32(oa + 3 * sa));
-                    const pk2 cb01 = pk(lds_f32(ob), lds_f32(ob + sb)), cb23 = pk(lds_f32(ob + 2 * sb), lds_f32(ob + 3 * sb));
-                    oa += 4 * sa;
-                    if (oa >= tt_end) oa -= 16u * D;
-                    ob += 4 * sb;
-                    if (ob >= tt_end) ob -= 16u * D;
-#pragma unroll
-                    for (int j = 0; j < N; ++j) {
-                        const float4 v = *reinterpret_cast<const float4 *>(yb + j * half);
-                        const pk2 v01 = pk(v.x, v.y), v23 = pk(v.z, v.w);
-                        aa[j][0] = fma2(v01, ca01, aa[j][0]);
-                        aa[j][1] = fma2(v23, ca23, aa[j][1]);
-                        ab[j][0] = fma2(v01, cb01, ab[j][0]);
-                        ab[j][1] = fma2(v23, cb23, ab[j][1]);
-                    }
-                    yb += 4;
-                };
                 auto flush = [&]() {
 #pragma unroll
                     for (int j = 0; j < N; ++j) {
@@ -540,28 +538,84 @@ __global__ void __launch_bounds__(WsCfg<K, DC, RIDER>::T, 1) fp_ws_kernel(const 
                         aa[j][0] = zero; aa[j][1] = zero; ab[j][0] = zero; ab[j][1] = zero;
                     }
                 };
-                int q = q0;
-                for (; q + 8 <= q1; q += 8) {             // 32 columns in float32 (4 chains of 8), then float64
+                auto advance = [&](unsigned int &o, unsigned int step) {
+                    o += 4 * step;
+                    if (o >= tend) o -= 8u * D;
+                };
+                if (odd) {
+                    // sin x at -D/2 entries for k = 1 (mod 4), -sin x at +D/2 entries for k = 3 (mod 4)
+                    const unsigned int shift = ((ka & 3) == 1) ? 6u * D : 2u * D;     // -2D or +2D bytes, modulo 8D
+                    unsigned int osa = oa + shift, osb = ob + shift;
+                    if (osa >= tend) osa -= 8u * D;
+                    if (osb >= tend) osb -= 8u * D;
+                    const float *yd = Yo + 4 * q0, *yr = Yo + N * quarter + 4 * q0;
+                    int q = q0;
+                    while (q < q1) {
+                        const int qe = min(q1, q + 4);              // 16 columns x (cos, sin) in float32, then float64
+                        for (; q < qe; ++q) {
+                            const pk2 ca01 = pk(lds_f32(oa), lds_f32(oa + sa)), ca23 = pk(lds_f32(oa + 2 * sa), lds_f32(oa + 3 * sa));
+                            const pk2 na01 = pk(lds_f32(osa), lds_f32(osa + sa)), na23 = pk(lds_f32(osa + 2 * sa), lds_f32(osa + 3 * sa));
+                            const pk2 cb01 = pk(lds_f32(ob), lds_f32(ob + sb)), cb23 = pk(lds_f32(ob + 2 * sb), lds_f32(ob + 3 * sb));
+                            const pk2 nb01 = pk(lds_f32(osb), lds_f32(osb + sb)), nb23 = pk(lds_f32(osb + 2 * sb), lds_f32(osb + 3 * sb));
+                            advance(oa, sa); advance(osa, sa); advance(ob, sb); advance(osb, sb);
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) quad();
-                    flush();
+                            for (int j = 0; j < N; ++j) {
+                                const float4 v = *reinterpret_cast<const float4 *>(yd + j * quarter);
+                                const float4 r = *reinterpret_cast<const float4 *>(yr + j * quarter);
+                                const pk2 v01 = pk(v.x, v.y), v23 = pk(v.z, v.w), r01 = pk(r.x, r.y), r23 = pk(r.z, r.w);
+                                aa[j][0] = fma2(v01, ca01, aa[j][0]);
+                                aa[j][1] = fma2(v23, ca23, aa[j][1]);
+                                aa[j][0] = fma2(r01, na01, aa[j][0]);
+                                aa[j][1] = fma2(r23, na23, aa[j][1]);
+                                ab[j][0] = fma2(v01, cb01, ab[j][0]);
+                                ab[j][1] = fma2(v23, cb23, ab[j][1]);
+                                ab[j][0] = fma2(r01, nb01, ab[j][0]);
+                                ab[j][1] = fma2(r23, nb23, ab[j][1]);
+                            }
+                            yd += 4;
+                            yr += 4;
+                        }
+                        flush();
+                    }
+                } else {
+                    const float *ye = Ye + (((ka & 3) == 0) ? 0 : N * quarter) + 4 * q0;      // EE or EO
+                    int q = q0;
+                    while (q < q1) {
+                        const int qe = min(q1, q + 8);              // 32 columns in float32 (4 chains of 8), then float64
+                        for (; q < qe; ++q) {
+                            const pk2 ca01 = pk(lds_f32(oa), lds_f32(oa + sa)), ca23 = pk(lds_f32(oa + 2 * sa), lds_f32(oa + 3 * sa));
+                            const pk2 cb01 = pk(lds_f32(ob), lds_f32(ob + sb)), cb23 = pk(lds_f32(ob + 2 * sb), lds_f32(ob + 3 * sb));
+                            advance(oa, sa); advance(ob, sb);
+#pragma unroll
+                            for (int j = 0; j < N; ++j) {
+                                const float4 v = *reinterpret_cast<const float4 *>(ye + j * quarter);
+                                const pk2 v01 = pk(v.x, v.y), v23 = pk(v.z, v.w);
+                                aa[j][0] = fma2(v01, ca01, aa[j][0]);
+                                aa[j][1] = fma2(v23, ca23, aa[j][1]);
+                                ab[j][0] = fma2(v01, cb01, ab[j][0]);
+                                ab[j][1] = fma2(v23, cb23, ab[j][1]);
+                            }
+                            ye += 4;
+                        }
+                        flush();
+                    }
                 }
-                if (q < q1) {
-                    for (; q < q1; ++q) quad();
-                    flush();
-                }
+                double *fp = (odd ? Fp : Fp + (size_t)DSo * N * H) + (size_t)ds * N * H;       // [ds][j][k slot]
 #pragma unroll
                 for (int j = 0; j < N; ++j) {
-                    Fp[((size_t)ds * N + j) * nk + (ka - 1)] = fa[j];
-                    if (hasb) Fp[((size_t)ds * N + j) * nk + (kb - 1)] = fb[j];
+                    fp[j * H + (ka - 1) / 2] = fa[j];
+                    if (hasb) fp[j * H + (kb - 1) / 2] = fb[j];
                 }
             }
             fin_bar();
             WS_ACC(t_2a);
             const bool layer_bad = s_flag != 0;       // read by everyone before thread 0 can start the next item
             for (int i = ftid; i < N * nk; i += NFT) {
+                const int j = i / nk, k = 1 + i % nk;
+                const double *fp = ((k & 1) ? Fp : Fp + (size_t)DSo * N * H) + j * H + (k - 1) / 2;
+                const int nds = (k & 1) ? DSo : DSe;
                 double f = 0.0;
-                for (int ds = 0; ds < DS; ++ds) f += Fp[(size_t)ds * N * nk + i];
+                for (int ds = 0; ds < nds; ++ds) f += fp[(size_t)ds * N * H];
                 Fr[i] = f;
             }
             fin_bar();
