@@ -443,8 +443,8 @@ __global__ void __launch_bounds__(WsCfg<K, DC, RIDER>::T, 1) fp_ws_kernel(const 
         double *Z = Fr + (size_t)N * nk;                   // [N][m]
         auto fin_bar = [&]() { named_bar_sync(1, NFT); };
 
-        // length-n inverse + per-column min-max of one column (fingerprint.py:138-140), y' - 0.5 as float
-        auto column = [&](const double (&u)[K], float (&yo)[N]) {
+        // length-n inverse + per-column min-max of one column (fingerprint.py:138-140): y' - 0.5
+        auto column = [&](const double (&u)[K], double (&yo)[N]) {
             double y[N];
             double mn = INFINITY, mx = -INFINITY;
             bool bad = false;
@@ -462,7 +462,7 @@ __global__ void __launch_bounds__(WsCfg<K, DC, RIDER>::T, 1) fp_ws_kernel(const 
             if (bad) s_flag = 1;       // constant / non-finite column: the reference yields NaN -> all 0
             const double inv = 1.0 / (mx - mn);
 #pragma unroll
-            for (int j = 0; j < N; ++j) yo[j] = (float)((y[j] - mn) * inv - 0.5);
+            for (int j = 0; j < N; ++j) yo[j] = (y[j] - mn) * inv - 0.5;
         };
         // Folded inputs of pass 2a from the u sums.  With x = pi (2d+1) k / 2D:
         //   cos at column D-1-d   = (-1)^k cos x                      -> e[d] = y'[d] + y'[D-1-d] (even k), o[d] = y'[d] - y'[D-1-d] (odd k), d < D/2
@@ -473,7 +473,7 @@ __global__ void __launch_bounds__(WsCfg<K, DC, RIDER>::T, 1) fp_ws_kernel(const 
         auto stage1 = [&](auto getu) {
             for (int d = ftid; d < quarter; d += NFT) {
                 const int c[4] = {d, half - 1 - d, half + d, D - 1 - d};
-                float y[4][N];
+                double y[4][N];            // folded in float64, rounded to float32 once
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     double u[K];
@@ -483,12 +483,12 @@ __global__ void __launch_bounds__(WsCfg<K, DC, RIDER>::T, 1) fp_ws_kernel(const 
                 }
 #pragma unroll
                 for (int j = 0; j < N; ++j) {
-                    const float e0 = y[0][j] + y[3][j], o0 = y[0][j] - y[3][j];      // columns d, D-1-d
-                    const float e1 = y[1][j] + y[2][j], o1 = y[1][j] - y[2][j];      // columns D/2-1-d, D/2+d
-                    Ye[j * quarter + d] = e0 + e1;
-                    Ye[(N + j) * quarter + d] = e0 - e1;
-                    Yo[j * quarter + d] = o0;
-                    Yo[(N + j) * quarter + d] = o1;
+                    const double e0 = y[0][j] + y[3][j], o0 = y[0][j] - y[3][j];     // columns d, D-1-d
+                    const double e1 = y[1][j] + y[2][j], o1 = y[1][j] - y[2][j];     // columns D/2-1-d, D/2+d
+                    Ye[j * quarter + d] = (float)(e0 + e1);
+                    Ye[(N + j) * quarter + d] = (float)(e0 - e1);
+                    Yo[j * quarter + d] = (float)o0;
+                    Yo[(N + j) * quarter + d] = (float)o1;
                 }
             }
         };
