@@ -14,7 +14,11 @@
 // Pass 1 is the HBM-bound part (every embedding element is read exactly once, n-1 FMAs each);
 // everything after it works on O(n*D) values per (domain, layer) and stays in shared memory.
 //
-// Kernel organisation (B200: 148 SMs, persistent CTAs pulling work items from an atomic queue):
+// Two kernels share the planner and the C ABI in this file: the warp-specialised TMA kernel of fp_ws_kernel.cuh
+// (the reference's configuration: n = 3, D = 1280 / 640, contiguous aligned rows) and the general kernel below
+// (every other shape; also the A/B partner, dctd_fp_set_variant(9)).
+//
+// General kernel (B200: 148 SMs, persistent CTAs pulling work items from an atomic queue):
 //   item = (domain, layer, row range <= 512 rows); a CTA streams the item's rows with 16-byte
 //   no-allocate loads, U rows in flight per thread, float32 FMAs flushed into float64
 //   accumulators every U rows; domains longer than 512 rows are split over several items whose
