@@ -16,6 +16,7 @@ Vectors must be integer valued in [-128, 127] - DCT fingerprints are int8 by con
 """
 from __future__ import annotations
 
+import os
 import struct
 
 import numpy as np
@@ -155,16 +156,39 @@ class IndexFlatL1(IndexFlat):
 _FOURCC = {METRIC_L2: b'IxF2', METRIC_INNER_PRODUCT: b'IxFI'}
 
 
-def write_index(index: IndexFlat, path: str):
+_SIDECAR_MAGIC = b'DCTDI8\x00\x01'
+
+
+def _sidecar_path(path: str) -> str:
+    return path + '.i8'
+
+
+def write_index(index: IndexFlat, path: str, sidecar: bool = None):
     """faiss.write_index for a flat index.  The file always records the metric the index was built
-    with (the reference builds IndexFlatL2 and flips to L1 only in memory, src/query_db.py:76)."""
+    with (the reference builds IndexFlatL2 and flips to L1 only in memory, src/query_db.py:76).
+
+    ``sidecar=True`` also writes ``<path>.i8``: the same vectors as raw int8 (a quarter of the bytes, no float
+    round trip on load).  ``read_index`` uses it when it matches the .index header (d, ntotal, file size of the
+    .index at the time of writing); the faiss-compatible .index stays the source of truth.  Default: off, or on
+    with DCTD_INDEX_SIDECAR=1 in the environment (so that the reference's unchanged ``faiss.write_index(index, path)``
+    at src/database.py:243 produces one)."""
+    if sidecar is None:
+        sidecar = os.environ.get('DCTD_INDEX_SIDECAR') == '1'
     metric = index.metric_type if index.metric_type in _FOURCC else METRIC_L2
-    data = index.reconstruct_n().astype(np.float32)
+    rows = index.reconstruct_n()
     with open(path, 'wb') as f:
         f.write(_FOURCC[metric])
         f.write(struct.pack('<iqqqBi', index.d, index.ntotal, 1 << 20, 1 << 20, 1, metric))
         f.write(struct.pack('<Q', index.ntotal * index.d))
-        f.write(data.tobytes())
+        f.write(rows.astype(np.float32).tobytes())
+    side = _sidecar_path(path)
+    if sidecar:
+        with open(side, 'wb') as f:
+            f.write(_SIDECAR_MAGIC)
+            f.write(struct.pack('<iqq', index.d, index.ntotal, os.path.getsize(path)))
+            f.write(np.ascontiguousarray(rows, dtype=np.int8).tobytes())
+    elif os.path.exists(side):
+        os.remove(side)                     # a stale sidecar must not outlive a rewritten index
 
 
 def read_index(path: str, device=None) -> IndexFlat:
@@ -179,7 +203,26 @@ def read_index(path: str, device=None) -> IndexFlat:
         (n_floats,) = struct.unpack('<Q', f.read(8))
         if n_floats != ntotal * d:
             raise ValueError(f'{path}: inconsistent header ({n_floats} floats for {ntotal} x {d})')
-        data = np.frombuffer(f.read(n_floats * 4), dtype='<f4').reshape(ntotal, d)
+        data = _read_sidecar(path, d, ntotal)
+        if data is None:
+            data = np.frombuffer(f.read(n_floats * 4), dtype='<f4').reshape(ntotal, d)
     index = IndexFlat(d, metric, device)
     index.add(data)
     return index
+
+
+def _read_sidecar(path: str, d: int, ntotal: int):
+    """int8 rows of ``<path>.i8`` if that file belongs to this .index (same d, ntotal and .index size), else None."""
+    side = _sidecar_path(path)
+    if not os.path.exists(side):
+        return None
+    with open(side, 'rb') as f:
+        if f.read(len(_SIDECAR_MAGIC)) != _SIDECAR_MAGIC:
+            return None
+        sd, sn, size = struct.unpack('<iqq', f.read(4 + 8 + 8))
+        if (sd, sn, size) != (d, ntotal, os.path.getsize(path)):
+            return None
+        raw = f.read(ntotal * d)
+    if len(raw) != ntotal * d:
+        return None
+    return np.frombuffer(raw, dtype=np.int8).reshape(ntotal, d)

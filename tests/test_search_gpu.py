@@ -100,6 +100,18 @@ def test_add_in_pieces_and_roundtrip(tmp_path):
     assert np.array_equal(im, im2) and np.array_equal(dm, dm2)
     with pytest.raises(ValueError):
         idx.add(np.full((1, 480), 0.5))        # not int8 valued
+    # int8 sidecar: used when it matches the .index, ignored (and removed on rewrite) otherwise
+    dindex.write_index(idx, path, sidecar=True)
+    assert os.path.getsize(path + '.i8') == 8 + 4 + 8 + 8 + 1000 * 480 and open(path, 'rb').read() == raw
+    side = dindex.read_index(path)
+    assert np.array_equal(side.reconstruct_n(), db)
+    with open(path + '.i8', 'r+b') as f:                      # corrupt the payload: proves the sidecar is what was read
+        f.seek(8 + 4 + 8 + 8)
+        f.write(bytes([db[0, 0] ^ 1]))
+    assert dindex.read_index(path).reconstruct_n()[0, 0] == (db[0, 0] ^ 1)
+    other = _index(db[:500])
+    dindex.write_index(other, path)                           # rewrite without a sidecar: the stale one goes away
+    assert not os.path.exists(path + '.i8') and dindex.read_index(path).ntotal == 500
 
 
 def test_empty_database_and_empty_queries():
