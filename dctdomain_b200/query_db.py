@@ -33,17 +33,47 @@ def get_top_hits(dm: np.ndarray, im: np.ndarray, top: int, fp_db, query_db, que_
         order = np.argsort(-flat_d, kind='stable')
     else:
         order = np.arange(flat_d.size)
-    select = """ SELECT pid, domain FROM fingerprints WHERE vid = ? """
     for rank, pos in enumerate(order[:top]):
         db_vid = int(flat_i[pos])
         if db_vid == -1:
             break
         q_vid = int(que_ind[pos // k])
-        db_pid, db_domain = fp_db.cur.execute(select, (db_vid + 1,)).fetchone()
-        q_pid, q_domain = query_db.cur.execute(select, (q_vid,)).fetchone()
+        db_pid, db_domain = _label(fp_db, db_vid + 1)
+        q_pid, q_domain = _label(query_db, q_vid)
         score = round(1 - (np.float32(flat_d[pos]) / 17000), 4)     # numpy float32, as the reference
         logging.info('Query: %s %s, Result %s: %s %s, Similarity: %s',
                      q_pid, q_domain, rank + 1, db_pid, db_domain, score)
+
+
+_SELECT = """ SELECT pid, domain FROM fingerprints WHERE vid = ? """
+
+
+def _label(db, vid: int):
+    """(pid, domain) of a fingerprint row: the reference's SELECT (src/query_db.py:50-57), answered from the labels
+    ``search_db`` fetched in bulk when there are any."""
+    cache = getattr(db, '_dctd_labels', None)
+    if cache is not None and vid in cache:
+        return cache[vid]
+    return db.cur.execute(_SELECT, (vid,)).fetchone()
+
+
+def _prefetch_labels(db, vids):
+    """One ``WHERE vid IN (...)`` query per 900 rows instead of one SELECT per hit (SQLite's default limit on bound
+    parameters is 999).  Objects that do not accept attributes simply keep answering row by row."""
+    vids = sorted({int(v) for v in vids})
+    try:
+        cache = getattr(db, '_dctd_labels', None)
+        if cache is None:
+            cache = {}
+            db._dctd_labels = cache
+    except AttributeError:
+        return
+    todo = [v for v in vids if v not in cache]
+    for a in range(0, len(todo), 900):
+        part = todo[a:a + 900]
+        marks = ','.join('?' * len(part))
+        for vid, pid, dom in db.cur.execute(f'SELECT vid, pid, domain FROM fingerprints WHERE vid IN ({marks})', part):
+            cache[int(vid)] = (pid, dom)
 
 
 def _open(db, database_cls):
@@ -78,6 +108,9 @@ def search_db(args: argparse.Namespace, query_db, fp_db, metric: str = 'l1', dat
         inds += [fp[0] for fp in qfps]
     if arrs:
         dm, im = index.search(np.array(arrs), args.khits)
+        # labels of everything that can be printed, fetched in bulk (reference: two SELECTs per hit, :50-57)
+        _prefetch_labels(fp_db, (im[im >= 0] + 1).ravel())
+        _prefetch_labels(query_db, inds)
         for b, e in spans:
             if e > b:
                 get_top_hits(dm[b:e], im[b:e], args.khits, fp_db, query_db, np.array(inds[b:e]), metric)

@@ -170,3 +170,22 @@ def test_topk_workspace_sizes_host_logic(lib):
     assert lib.dctd_l1_topk_workspace_bytes(8, 1000, 4096, 10) == 0      # d limit
     assert lib.dctd_l1_topk_workspace_bytes(8, 1000, 1024, 10) > 0       # wide vectors: one group per stage
     assert lib.dctd_l1_packed_bytes(33, 480) == 64 * 480 and lib.dctd_l1_packed_bytes(1, 100) == 32 * 112
+
+
+def test_search_db_label_prefetch_matches_row_by_row_selects(tmp_path):
+    """search_db fetches the (pid, domain) labels of all hits with WHERE vid IN (...) queries; get_top_hits then
+    answers from that cache - same tuples as the reference's per-hit SELECT (src/query_db.py:50-57)."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from minidb import MiniDB
+    from dctdomain_b200 import query_db as qdb
+    npz = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'example-dct.npz'))
+    db = MiniDB(str(tmp_path / 'x.db'), npz)
+    n = len(npz['dom'])
+    want = {vid: db.cur.execute(qdb._SELECT, (vid,)).fetchone() for vid in range(1, n + 1)}
+    assert qdb._label(db, 7) == want[7]                        # no cache yet: row-by-row path
+    qdb._prefetch_labels(db, list(range(1, n + 1)) * 30)       # duplicates and > 900 bound parameters' worth of input
+    assert db._dctd_labels == want
+    db.cur.execute('DELETE FROM fingerprints')                 # answers now come from the cache only
+    assert all(qdb._label(db, vid) == want[vid] for vid in want)
+    db.close()
