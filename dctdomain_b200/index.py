@@ -222,7 +222,7 @@ def _read_sidecar(path: str, d: int, ntotal: int):
         sd, sn, size = struct.unpack('<iqq', f.read(4 + 8 + 8))
         if (sd, sn, size) != (d, ntotal, os.path.getsize(path)):
             return None
-        raw = f.read(ntotal * d)
-    if len(raw) != ntotal * d:
+        rows = np.fromfile(f, dtype=np.int8, count=ntotal * d)      # writable: torch.from_numpy takes it as is
+    if rows.size != ntotal * d:
         return None
-    return np.frombuffer(raw, dtype=np.int8).reshape(ntotal, d)
+    return rows.reshape(ntotal, d)
