@@ -189,3 +189,107 @@ def test_search_db_label_prefetch_matches_row_by_row_selects(tmp_path):
     db.cur.execute('DELETE FROM fingerprints')                 # answers now come from the cache only
     assert all(qdb._label(db, vid) == want[vid] for vid in want)
     db.close()
+
+
+@pytest.mark.parametrize('seed', range(6))
+def test_planner_fuzz_items_cover_every_domain_row_once(lib, seed):
+    """Random geometry (windows, multi-segment / overlapping domains, fusion candidates): walking the runs of every
+    item record - first run from the record, later runs from the piece list clipped to the item's row range, exactly
+    what the producer warp of the warp-specialised kernel does - must visit the rows of each (domain, layer) in order
+    with the right protein position; for a fused protein, rider items and filler items together visit every protein
+    row exactly once per layer."""
+    rs = np.random.RandomState(seed)
+    maxlen, overlap = 500, 200
+    stride = maxlen - overlap
+    src_rows, prot_src0, prot_nsrc, plens = [], [], [], []
+    for p in range(12):
+        prot_src0.append(len(src_rows))
+        Lp = int(rs.choice([rs.randint(3, 80), rs.randint(80, 500), rs.randint(501, 2200)]))
+        if Lp <= maxlen or rs.rand() < 0.3:
+            src_rows.append(Lp)
+        else:
+            start = 0
+            while True:
+                rows = min(maxlen, Lp - start)
+                if start > 0 and rows <= overlap:
+                    break
+                src_rows.append(rows)
+                if start + rows >= Lp:
+                    break
+                start += stride
+        prot_nsrc.append(len(src_rows) - prot_src0[-1])
+        plens.append(src_rows[-1] if prot_nsrc[-1] == 1 else (prot_nsrc[-1] - 1) * stride + src_rows[-1])
+    dom_prot, seg_off, sb, se = [], [0], [], []
+    for p, Lp in enumerate(plens):
+        doms = []
+        if rs.rand() < 0.5 and Lp >= 12:
+            cuts = sorted(rs.choice(np.arange(3, Lp - 3), size=min(rs.randint(1, 5), max(1, (Lp - 6) // 4)), replace=False))
+            edges = [0] + [int(c) for c in cuts] + [Lp]
+            doms = [[(a, b)] for a, b in zip(edges[:-1], edges[1:]) if b - a >= 3]
+            if rs.rand() < 0.5 and len(doms) > 1:
+                doms.pop(rs.randint(len(doms)))
+            doms.append([(0, Lp)])
+        else:
+            for _ in range(rs.randint(1, 4)):
+                segs = []
+                for _ in range(rs.randint(1, 4)):
+                    a = rs.randint(0, Lp)
+                    segs.append((a, rs.randint(a + 1, Lp + 1)))
+                if sum(b - a for a, b in segs) >= 3:
+                    doms.append(segs)
+            if not doms:
+                doms.append([(0, Lp)])
+        for segs in doms:
+            dom_prot.append(p)
+            for a, b in segs:
+                sb.append(a); se.append(b)
+            seg_off.append(len(sb))
+    n_layers = 2
+    plan = _plan(lib, n_layers=n_layers, D=1280, n=3, m=80, src_rows=src_rows, prot_src0=prot_src0, prot_nsrc=prot_nsrc,
+                 dom_prot=dom_prot, dom_seg_off=seg_off, seg_beg=sb, seg_end=se, maxlen=maxlen, overlap=overlap)
+    pieces, items = _dump(lib, plan)
+    rec = _records(lib, plan, len(items))
+    rider_targets = {int(r[W['rider_dom']]) for r in rec if r[W['flags']] & F_RIDER}     # fused global domains
+
+    def runs_of(r):
+        out = []
+        for run in range(r[W['n_runs']]):
+            if run == 0:
+                out.append(tuple(int(r[W[k]]) for k in ('run_src_a', 'run_row_a', 'run_src_b', 'run_row_b', 'run_rows',
+                                                        'run_l0', 'run_g0')))
+            else:
+                sa, ra, sb_, rb, nrows, l0, g0 = (int(x) for x in pieces[r[W['piece_abs']] + run])
+                a, b = max(l0, int(r[W['r0']])), min(l0 + nrows, int(r[W['r1']]))
+                out.append((sa, ra + a - l0, sb_, rb + a - l0, b - a, a, g0 + a - l0))
+        return out
+
+    def protein_row(p, src, row):          # protein row that (source, row) holds
+        return row if prot_nsrc[p] == 1 else (src - prot_src0[p]) * stride + row
+
+    covered = {}
+    for r in rec:
+        dom, layer = int(r[W['dom']]), int(r[W['layer']])
+        p = dom_prot[dom]
+        expect = [x for j in range(seg_off[dom], seg_off[dom + 1]) for x in range(sb[j], se[j])]   # domain rows in order
+        filler = dom in rider_targets          # a fused global domain streams only the rows nobody else covers
+        pos = int(r[W['r0']])
+        for sa, ra, sb_, rb, nrows, l0, g0 in runs_of(r):
+            assert nrows > 0 and l0 >= pos
+            if not filler:
+                assert l0 == pos
+            for t in range(nrows):
+                prow = protein_row(p, sa, ra + t)
+                assert prow == g0 + t
+                if sb_ >= 0:                   # the same protein row seen through the next window
+                    assert protein_row(p, sb_, rb + t) == prow and sb_ == sa + 1
+                assert expect[l0 + t] == prow
+                if filler or (r[W['flags']] & F_RIDER):
+                    covered.setdefault((p, layer), []).append(prow)
+            pos = l0 + nrows
+        if not filler:
+            assert pos == r[W['r1']]
+        if r[W['flags']] & F_RIDER:
+            assert r[W['Lg']] == plens[p] and dom_prot[int(r[W['rider_dom']])] == p
+    for (p, layer), rows in covered.items():
+        assert sorted(rows) == list(range(plens[p])), (p, layer)
+    assert len(covered) == n_layers * len({dom_prot[d] for d in rider_targets})
