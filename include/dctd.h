@@ -11,7 +11,9 @@
  *     named h_* / "host" are host pointers; the caller owns every buffer including workspaces;
  *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); all device work
  *     is stream-ordered on it and the functions do not synchronise unless stated;
- *   - the library keeps no global mutable state besides a thread-local "last CUDA error".
+ *   - the library keeps no global mutable state besides a thread-local "last CUDA error" and launch counter.
+ *     (The tuning / test hooks that are NOT declared here - dctd_fp_set_variant, dctd_fp_set_fusion, dctd_l1_set_mode,
+ *     dctd_fp_plan_dump*, dctd_fp_timing_read - flip process-global switches; they exist for A/B runs and tests only.)
  */
 #ifndef DCTD_H
 #define DCTD_H
