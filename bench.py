@@ -10,8 +10,14 @@ Primary line = BASELINE.json metric part (i), domain fingerprints/s, on configs[
   default 200 steps stream 819,200 domains (8x the 100k of configs[1], ~0.4 s timed).  `value` times the kernel path with inputs resident in
   HBM; `e2e` times the public Python API (`quantize_batch` on Fingerprint objects) with pinned host
   embeddings, H2D + kernel + D2H inside the timed region.
-The same JSON line carries `search`: part (ii) of the metric, L1 top-50 query.DB pairs/s on a
-1M-fingerprint database (configs[3] size), sharded over the N ranks with an NCCL all-gather merge.
+The same JSON line carries part (ii) of the metric, L1 top-50 query.DB pairs/s, with the database sharded over the
+N ranks (contiguous ranges, NCCL exchange of packed keys, merge by (distance, position)):
+  `search`          configs[4]: 10k-query batch x 50M fingerprints (24 GB)
+  `search_1m`       8192-query batch x 1M fingerprints (configs[3] size) + the CPU restatement timed beside it
+  `search_allvsall` configs[3] in full: 1M x 1M, one pass, results distributed by query slice (all_to_all)
+  `search_stream`   the HBM-bound regime: 8 queries per call x the configs[4] shards (roofline: HBM)
+each with `parity`: the result of the timed call compared bit for bit with the oracle over the whole database on a
+subsample of the queries.
 """
 from __future__ import annotations
 
@@ -199,10 +205,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
-        # stdout carries exactly one JSON line: NCCL prints its version banner there at any NCCL_DEBUG level
-        os.environ.pop('NCCL_DEBUG', None)
-        if os.environ.get('DCTD_NCCL_DEBUG'):
-            os.environ['NCCL_DEBUG'] = os.environ['DCTD_NCCL_DEBUG']
+        # NCCL_DEBUG is left as the caller set it (the driver reads the rank count from NCCL's own log)
         dist.init_process_group('nccl', device_id=dev)
 
     def barrier():
@@ -327,15 +330,28 @@ def run_ours(args):
         longseq = run_windows(torch, dev, rank, make_plan, execute_plan, barrier, max_over_ranks, world, peak)
 
     # ---- search: part (ii) of the metric ----
-    search = None
+    cores = os.cpu_count() or 1
+    search = search_1m = allvsall = stream = None
     if not args.no_search:
-        search = run_search(args, dev, rank, world, dist, torch, dindex, ShardedIndex, shard_bounds, synth, barrier,
-                            max_over_ranks, L, peak)
-
-    # ---- search, streaming regime (HBM-bound): a reference-style call, 8 queries against a configs[4] shard ----
-    stream = None
-    if not args.no_search and world == 1:
-        stream = run_search_stream(args, dev, torch, dindex, L, peak)
+        common = (dev, rank, world, dist, torch, barrier, max_over_ranks, L, cores)
+        # configs[3]-sized database: a batch of 8192 queries, then the full all-vs-all pass
+        sh1, rows1 = build_sharded(torch, dev, ShardedIndex, args.search_db, rank, world, 4242, keep_rows=True)
+        q1 = perturbed_queries(torch, dev, dist, sh1, args.search_queries, rank, world, 7)
+        search_1m = run_search(args, 'configs[3]-sized', sh1, q1, max(2, min(args.steps, 5)), 64, *common)
+        if not args.no_allvsall:
+            allvsall = run_allvsall(args, sh1, rows1, *common)
+        del sh1, rows1, q1
+        torch.cuda.empty_cache()
+        if not args.no_cfg4:
+            # configs[4]: 50M fingerprints (24 GB), 10k-query batch; then the streaming regime on the same shards
+            sh4, _ = build_sharded(torch, dev, ShardedIndex, args.cfg4_db, rank, world, 99)
+            q4 = perturbed_queries(torch, dev, dist, sh4, args.cfg4_queries, rank, world, 8)
+            search = run_search(args, 'configs[4]', sh4, q4, 2, 8, *common)
+            stream = run_search_stream(args, sh4, dev, rank, world, dist, torch, barrier, max_over_ranks, L, peak, cores)
+            del sh4, q4
+            torch.cuda.empty_cache()
+        else:
+            search = search_1m
 
     # ---- CPU baseline (rank 0, N = 1 only) ----
     cpu = None
@@ -346,8 +362,8 @@ def run_ours(args):
         n = int(min(max(r0 * 12.0, cores * 4), 20000))                # ~12 s of CPU work
         r, dt = arm.rate(n)
         arm.close()
-        if search is not None:
-            search['cpu_baseline'] = cpu_search_rate(cores)
+        if search_1m is not None:
+            search_1m['cpu_baseline'] = cpu_search_rate(cores)
         cpu = {'value': r, 'unit': 'fingerprints/s', 'cores': cores, 'kind': 'port', 'seconds': dt,
                'sample': f'{n} domains, L~U{{{LMIN}..{LMAX}}}, {LAYERS}x{D} fp32: oracle port of reference '
                          f'fingerprint.py quantize under multiprocessing.Pool({cores}) (embeddings pre-forked, not pickled)'}
@@ -361,11 +377,23 @@ def run_ours(args):
                        'l2': 'inputs larger than L2 (each step streams ~%.1f GB)' % (sum(algo) / len(algo) / 1e9),
                        'parallelism': f'domains sharded over {world} rank(s), no collective'},
             'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches, 'roofline': roofline, 'cpu_baseline': cpu,
-            'protein_batch': fused, 'long_sequences': longseq, 'search': search, 'search_stream': stream,
+            'protein_batch': fused, 'long_sequences': longseq, 'search': search, 'search_1m': search_1m,
+            'search_allvsall': allvsall, 'search_stream': stream,
+            # part (ii) of the metric, for the strong-scaling curve (the primary line above is collective-free by nature)
+            'search_scaling_input': None if search is None else {
+                'metric': search['metric'], 'value': search['value'], 'unit': 'pairs/s', 'scaling': 'strong',
+                'n_gpus': world, 'workload': search['config']['workload'], 'parity_mismatches': search['parity']['mismatches']},
         }
-        print(json.dumps(line), flush=True)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
+    if rank == 0:
+        # the JSON line is the LAST thing on stdout: NCCL_DEBUG output (left as the caller set it) goes to the same
+        # stream from every rank, so the other ranks have finished and the group is torn down before it is printed
+        if world > 1:
+            time.sleep(1.0)
+        sys.stdout.flush()
+        print(json.dumps(line), flush=True)
 
 
 def run_fused(torch, dev, rank, make_plan, execute_plan, barrier, max_over_ranks, world, peak):
@@ -469,27 +497,113 @@ def run_windows(torch, dev, rank, make_plan, execute_plan, barrier, max_over_ran
                                  'riding global fingerprint add no reads'}}
 
 
-def run_search(args, dev, rank, world, dist, torch, dindex, ShardedIndex, shard_bounds, synth, barrier,
-               max_over_ranks, L, peak):
-    n_db, nq, k = args.search_db, args.search_queries, 50
-    b, e = shard_bounds(n_db, world, rank)
-    # synthetic fingerprints generated on the device per shard (values 0..127, like real ones)
-    shard = synth_shard(torch, dev, e - b, 4242 + rank)
+SLICE = 1 << 20     # rows generated / copied per piece
+
+
+def synth_rows(torch, dev, n, seed):
+    """n synthetic int8[480] fingerprints on the device (values 0..127, clip(N(63.6, 27.7)) like real ones)."""
+    g = torch.Generator(device=dev).manual_seed(seed)
+    return torch.clamp(torch.randn((n, 480), generator=g, device=dev) * 27.7 + 63.6, 0, 127).round().to(torch.int8)
+
+
+def build_sharded(torch, dev, ShardedIndex, n_db, rank, world, seed, keep_rows=False):
+    """This rank's contiguous shard of an n_db-row database, generated on the device piece by piece."""
     sh = ShardedIndex(480, n_db, rank=rank, world=world, device=dev)
-    sh.index.add(shard)
-    # queries: perturbed rows of rank 0's shard, replicated
-    gq = torch.Generator(device=dev).manual_seed(7)
+    n_local = sh.end - sh.begin
+    sh.index.reserve(n_local)
+    kept = []
+    for a in range(0, n_local, SLICE):
+        rows = synth_rows(torch, dev, min(SLICE, n_local - a), seed * 1000003 + rank * 7919 + a // SLICE)
+        sh.index.add(rows)
+        if keep_rows:
+            kept.append(rows)
+    return sh, (torch.cat(kept) if keep_rows and kept else None)
+
+
+def perturbed_queries(torch, dev, dist, sh, nq, rank, world, seed):
+    """Queries = perturbed rows of rank 0's shard (so that true neighbours and ties exist), replicated."""
     if rank == 0:
-        rows = torch.randint(0, e - b, (nq,), generator=gq, device=dev)
-        q = torch.clamp(shard[rows].to(torch.int16) + torch.randint(-3, 4, (nq, 480), generator=gq, device=dev).to(torch.int16),
+        g = torch.Generator(device=dev).manual_seed(seed)
+        pool_n = min(sh.end - sh.begin, SLICE)
+        pool = torch.from_numpy(sh.index.reconstruct_n(0, pool_n)).to(dev)
+        rows = torch.randint(0, pool_n, (nq,), generator=g, device=dev)
+        q = torch.clamp(pool[rows].to(torch.int16) + torch.randint(-3, 4, (nq, 480), generator=g, device=dev).to(torch.int16),
                         0, 127).to(torch.int8)
     else:
         q = torch.empty((nq, 480), dtype=torch.int8, device=dev)
     if world > 1:
         dist.broadcast(q, 0)
-    steps = max(2, min(args.steps, 5))
-    for _ in range(3):
-        sh.search(q, k)
+    return q
+
+
+def oracle_topk_sharded(torch, dist, dev, sh, q_host, k, world, threads):
+    """The oracle (oracle/l1_flat.c, faiss flat-L1 restated) over the WHOLE database: every rank scans its own shard
+    piece by piece on the host, the per-rank lists are exchanged and merged by (distance, id) with numpy.  Collective:
+    all ranks call it with the same queries.  This is the checker, never the thing measured."""
+    from oracle import search_oracle as so
+    m = len(q_host)
+    big = np.iinfo(np.int64).max
+
+    def merge(d, i):
+        order = np.lexsort((np.where(i < 0, big, i), d), axis=1)[:, :k]
+        return np.take_along_axis(d, order, 1), np.take_along_axis(i, order, 1)
+
+    bd = np.full((m, k), so.FLT_MAX, dtype=np.float32)
+    bi = np.full((m, k), -1, dtype=np.int64)
+    n_local = sh.end - sh.begin
+    for a in range(0, n_local, SLICE):
+        rows = sh.index.reconstruct_n(a, min(SLICE, n_local - a))
+        d, i = so.l1_topk(q_host, rows, k, threads=threads)
+        i = np.where(i >= 0, i + sh.begin + a, -1)
+        bd, bi = merge(np.concatenate([bd, d], 1), np.concatenate([bi, i], 1))
+    if world > 1:
+        td, ti = torch.from_numpy(bd).to(dev), torch.from_numpy(bi).to(dev)
+        ad = torch.empty((world,) + td.shape, dtype=td.dtype, device=dev)
+        ai = torch.empty((world,) + ti.shape, dtype=ti.dtype, device=dev)
+        dist.all_gather_into_tensor(ad, td)
+        dist.all_gather_into_tensor(ai, ti)
+        bd, bi = merge(ad.permute(1, 0, 2).reshape(m, world * k).cpu().numpy(),
+                       ai.permute(1, 0, 2).reshape(m, world * k).cpu().numpy())
+    return bd, bi
+
+
+def parity_record(got_d, got_i, want_d, want_i, note):
+    bad = int((~((got_i == want_i).all(axis=1) & (got_d == want_d).all(axis=1))).sum())
+    return {'checked': int(len(want_i)), 'mismatches': bad,
+            'oracle': 'oracle/l1_flat.c (faiss 1.7.4 flat-L1 restated) over the full database, shard by shard, merged '
+                      'by (distance, id) with numpy; compared bit for bit (ids and float32 distances)', 'queries': note}
+
+
+def phase_ms(sh, fn):
+    """Per-step CUDA-event times of one call of fn() (ShardedIndex marks an event after every step)."""
+    sh.events = []
+    fn()
+    import torch
+    torch.cuda.synchronize()
+    ev, out = sh.events, {}
+    sh.events = None
+    for (n0, e0), (n1, e1) in zip(ev[:-1], ev[1:]):
+        if n1 != 'start':
+            out[n1] = out.get(n1, 0.0) + e0.elapsed_time(e1)
+    return out
+
+
+def search_roofline(pairs, ms_total, db_bytes_rank, world):
+    sad_peak = SAD4_PEAK_PER_GPU * world          # scripts/microbench/sad_peak.cu, profiles/sad_peak.json
+    sad_rate = pairs * 120 / (ms_total * 1e-3)
+    return {'bound': 'integer pipe (VABSDIFF4.U8.ACC, 120 per pair; not HBM: the shard streams at %.1f GB/s per rank)'
+                     % (db_bytes_rank / (ms_total * 1e-3) / 1e9),
+            'achieved': sad_rate, 'peak': sad_peak, 'unit': 'SAD4 lane-ops/s', 'frac': sad_rate / sad_peak,
+            'peak_source': 'measured VABSDIFF4 issue peak, 63 lanes/clk/SM x 148 SMs x 1.965 GHz '
+                           '(scripts/microbench/sad_peak.cu)'}
+
+
+def run_search(args, tag, sh, q, steps, parity_q, dev, rank, world, dist, torch, barrier, max_over_ranks, L, cores):
+    """Part (ii) of the metric on one sharded database: timed ShardedIndex.search (queries and shard in HBM), the
+    per-step times of one call, the same call through the host-array API (e2e) and the oracle comparison."""
+    n_db, nq, k = sh.n_total, int(q.shape[0]), 50
+    for _ in range(2):
+        dd, ii = sh.search(q, k)
     barrier()
     L.dctd_launch_count(1)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -500,80 +614,133 @@ def run_search(args, dev, rank, world, dist, torch, dindex, ShardedIndex, shard_
     barrier()
     ms = max_over_ranks(ev0.elapsed_time(ev1))
     launches = int(L.dctd_launch_count(0))
+    path = sh.last_path
+    phases = phase_ms(sh, lambda: sh.search(q, k))
     pairs = float(nq) * n_db * steps
-    # e2e: host queries in, host results out (faiss-style index.search), single rank semantics
+    # e2e: host queries in, host results out on every rank (faiss-style index.search)
     qh = q.cpu().numpy()
+    sh.search(qh, k)
+    barrier()
     t0 = time.perf_counter()
-    if world == 1:
-        for _ in range(steps):
-            sh.index.search(qh, k)
-        torch.cuda.synchronize()
-        e2e_pairs = pairs / (time.perf_counter() - t0)
-    else:
-        e2e_pairs = None
-    db_bytes = (e - b) * 480
-    sad_peak = SAD4_PEAK_PER_GPU * world          # scripts/microbench/sad_peak.cu, profiles/sad_peak.json
-    sad_rate = pairs * 120 / (ms * 1e-3)
+    for _ in range(steps):
+        hd, hi = sh.search(qh, k)
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    # parity on a subsample of the queries against the oracle over the full database
+    rs = np.random.RandomState(17)
+    sel = np.sort(rs.choice(nq, size=min(parity_q, nq), replace=False))
+    want_d, want_i = oracle_topk_sharded(torch, dist, dev, sh, qh[sel], k, world, max(1, cores // world))
+    parity = parity_record(hd[sel], hi[sel], want_d, want_i, f'{len(sel)} of the {nq} timed queries (host-array API result)')
+    dev_same = bool(np.array_equal(dd.cpu().numpy(), hd) and np.array_equal(ii.cpu().numpy(), hi))
+    parity['device_api_equals_host_api'] = dev_same
     return {'metric': 'L1 top-50 query.DB pairs/s', 'value': pairs / (ms * 1e-3), 'unit': 'pairs/s', 'ms_per_step': ms / steps,
-            'steps': steps, 'scaling': 'strong', 'dtype': 'u8', 'gpu_launches': launches,
-            'config': {'workload': f'{"configs[4]" if n_db >= 50_000_000 else "configs[3]"}-sized: {nq} queries x {n_db} '
-                                   f'int8[480] fingerprints, k=50, DB sharded over {world} rank(s), NCCL all-gather merge',
+            'steps': steps, 'scaling': 'strong', 'dtype': 'u8', 'gpu_launches': launches, 'n_gpus': world,
+            'config': {'workload': f'{tag}: {nq} queries x {n_db} int8[480] fingerprints, k=50, database sharded over '
+                                   f'{world} rank(s) (contiguous ranges), exchange: {path}',
                        'n_db': n_db, 'nq': nq, 'k': k},
-            'e2e_pairs_per_s': e2e_pairs,
-            'roofline': {'bound': 'integer pipe (VABSDIFF4.U8.ACC, 120 per pair; not HBM: the database streams at '
-                                  '%.1f GB/s per rank)' % (db_bytes / (ms / steps * 1e-3) / 1e9),
-                         'achieved': sad_rate, 'peak': sad_peak, 'unit': 'SAD4 lane-ops/s', 'frac': sad_rate / sad_peak,
-                         'peak_source': 'measured VABSDIFF4 issue peak, 63 lanes/clk/SM x 148 SMs x 1.965 GHz '
-                                        '(scripts/microbench/sad_peak.cu)'}}
+            'phases_ms': phases,
+            'e2e': {'value': pairs / e2e_s, 'unit': 'pairs/s', 'h2d_bytes_per_step': nq * 480, 'd2h_bytes_per_step': nq * k * 12,
+                    'api': 'ShardedIndex.search(numpy queries, k) -> numpy (dist, ids) on every rank'},
+            'e2e_pairs_per_s': pairs / e2e_s,
+            'parity': parity,
+            'roofline': search_roofline(pairs, ms, (sh.end - sh.begin) * 480 * steps, world)}
 
 
-def synth_shard(torch, dev, n, seed):
-    """n synthetic int8[480] fingerprints on the device (values 0..127 like real ones), generated in slices."""
-    g = torch.Generator(device=dev).manual_seed(seed)
-    out = torch.empty((n, 480), dtype=torch.int8, device=dev)
-    step = 1 << 20
-    for a in range(0, n, step):
-        b = min(n, a + step)
-        out[a:b] = torch.clamp(torch.randn((b - a, 480), generator=g, device=dev) * 27.7 + 63.6, 0, 127).round().to(torch.int8)
-    return out
+def run_allvsall(args, sh, rows_local, dev, rank, world, dist, torch, barrier, max_over_ranks, L, cores):
+    """configs[3] in full: every fingerprint of the database against the whole database, top-50.  Queries go through in
+    batches of 8192; every rank scans its shard for the whole batch and merges / keeps the results of its slice of the
+    batch (all_to_all of the packed keys)."""
+    n_db, k, B = sh.n_total, 50, 8192
+    if n_db % world:
+        return None
+    if world > 1:
+        allrows = torch.empty((n_db, 480), dtype=torch.int8, device=dev)
+        dist.all_gather_into_tensor(allrows, rows_local.contiguous())
+    else:
+        allrows = rows_local
+    sh.search_slice(allrows[:B], k)                     # warm-up of this code path
+    barrier()
+    L.dctd_launch_count(1)
+    keep = None
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for b in range(0, n_db, B):
+        r = sh.search_slice(allrows[b:b + B], k)
+        if b == 0:
+            keep = r
+    ev1.record()
+    barrier()
+    ms = max_over_ranks(ev0.elapsed_time(ev1))
+    launches = int(L.dctd_launch_count(0))
+    path = sh.last_path
+    # parity: 4 queries of every rank's slice of the first batch
+    per = -(-min(B, n_db) // world)
+    sel = np.concatenate([np.arange(j * per, j * per + 4) for j in range(world)])
+    want_d, want_i = oracle_topk_sharded(torch, dist, dev, sh, allrows[sel].cpu().numpy(), k, world, max(1, cores // world))
+    dm, im, qb, qe = keep
+    mine = slice(rank * 4, rank * 4 + 4)
+    rec = parity_record(dm[:4].cpu().numpy(), im[:4].cpu().numpy(), want_d[mine], want_i[mine], '')
+    bad = torch.tensor([rec['mismatches']], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(bad)
+    rec.update(checked=4 * world, mismatches=int(bad.item()),
+               queries='4 queries of every rank\'s slice of the first batch (each rank checks the rows it keeps)')
+    pairs = float(n_db) * n_db
+    return {'metric': 'L1 top-50 query.DB pairs/s (all-vs-all)', 'value': pairs / (ms * 1e-3), 'unit': 'pairs/s',
+            'seconds': ms * 1e-3, 'batches': -(-n_db // B), 'scaling': 'strong', 'dtype': 'u8', 'gpu_launches': launches,
+            'n_gpus': world,
+            'config': {'workload': f'configs[3]: all-vs-all L1 top-50 over {n_db} int8[480] fingerprints, one full pass, '
+                                   f'database sharded over {world} rank(s), results distributed by query slice, exchange: {path}',
+                       'n_db': n_db, 'nq': n_db, 'k': k},
+            'parity': rec, 'roofline': search_roofline(pairs, ms, (sh.end - sh.begin) * 480 * (-(-n_db // B)), world)}
 
 
-def run_search_stream(args, dev, torch, dindex, L, peak):
-    n_db, nq, k = args.stream_db, 8, 50
-    idx = dindex.IndexFlatL2(480)
-    idx.metric_type = dindex.METRIC_L1
-    idx.add(synth_shard(torch, dev, n_db, 99))
-    q = synth_shard(torch, dev, nq, 5)
+def run_search_stream(args, sh, dev, rank, world, dist, torch, barrier, max_over_ranks, L, peak, cores):
+    """The HBM-bound regime: a reference-style call (8 query fingerprints, src/query_db.py:87) against the sharded
+    configs[4] database; per call every rank streams its shard once, then all_gather + merge."""
+    n_db, nq, k = sh.n_total, 8, 50
+    q = synth_rows(torch, dev, nq, 5)
+    if world > 1:
+        dist.broadcast(q, 0)
     for _ in range(3):
-        idx.search_device(q, k)
-    torch.cuda.synchronize()
+        sh.search(q, k)
+    barrier()
     steps = 20
     L.dctd_launch_count(1)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(steps):
-        idx.search_device(q, k)
+        dd, ii = sh.search(q, k)
     e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / steps
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1)) / steps
     launches = int(L.dctd_launch_count(0))
+    path = sh.last_path
+    phases = phase_ms(sh, lambda: sh.search(q, k))
     qh = q.cpu().numpy()                     # e2e: faiss-style index.search(host int8 array) -> host arrays
-    idx.search(qh, k)
+    sh.search(qh, k)
+    barrier()
     t0 = time.perf_counter()
     for _ in range(steps):
-        idx.search(qh, k)
-    e2e_ms = (time.perf_counter() - t0) / steps * 1e3
-    db_bytes = n_db * 480
-    gbs = db_bytes / ms / 1e6
+        hd, hi = sh.search(qh, k)
+    barrier()
+    e2e_ms = max_over_ranks(time.perf_counter() - t0) / steps * 1e3
+    want_d, want_i = oracle_topk_sharded(torch, dist, dev, sh, qh, k, world, max(1, cores // world))
+    parity = parity_record(hd, hi, want_d, want_i, 'all 8 queries')
+    shard_bytes = (sh.end - sh.begin) * 480
+    gbs = shard_bytes / ms / 1e6
     return {'metric': 'L1 top-50 query.DB pairs/s (streaming regime)', 'value': nq * n_db / ms * 1e3, 'unit': 'pairs/s',
-            'ms_per_step': ms, 'steps': steps, 'dtype': 'u8', 'gpu_launches': launches,
-            'e2e_pairs_per_s': nq * n_db / e2e_ms * 1e3, 'e2e_ms_per_call': e2e_ms,
+            'ms_per_step': ms, 'steps': steps, 'dtype': 'u8', 'gpu_launches': launches, 'n_gpus': world,
+            'e2e_pairs_per_s': nq * n_db / e2e_ms * 1e3, 'e2e_ms_per_call': e2e_ms, 'phases_ms': phases, 'parity': parity,
             'config': {'workload': f'{nq} queries per call (the reference calls index.search with 1-13, src/query_db.py:87) x '
-                                   f'{n_db} int8[480] fingerprints (one configs[4] shard, {db_bytes / 1e9:.1f} GB >> L2), k=50',
+                                   f'{n_db} int8[480] fingerprints sharded over {world} rank(s) ({shard_bytes / 1e9:.1f} GB per '
+                                   f'rank >> L2), k=50, exchange: {path}',
                        'n_db': n_db, 'nq': nq, 'k': k},
-            'roofline': {'bound': 'hbm', 'achieved': gbs, 'peak': peak, 'unit': 'GB/s', 'frac': gbs / peak,
-                         'algorithmic_bytes_per_launch': db_bytes,
-                         'kernel': 'l1_thresh_stream_kernel (csrc/l1topk.cu), database streamed once per call'}}
+            'roofline': {'bound': 'hbm', 'achieved': gbs, 'peak': peak, 'unit': 'GB/s per GPU', 'frac': gbs / peak,
+                         'algorithmic_bytes_per_launch': shard_bytes,
+                         'note': 'per rank: shard bytes / time of the WHOLE call (threshold sample, stream, select, NCCL '
+                                 'all-gather, merge), max over ranks',
+                         'kernel': 'l1 streaming kernel (csrc/l1topk.cu), every shard streamed once per call'}}
 
 
 def cpu_search_rate(cores):
@@ -610,7 +777,10 @@ def main():
     ap.add_argument('--e2e-batch', type=int, default=512)
     ap.add_argument('--search-db', type=int, default=1_000_000)
     ap.add_argument('--search-queries', type=int, default=8192)
-    ap.add_argument('--stream-db', type=int, default=6_250_000, help='database size of the streaming-regime search line')
+    ap.add_argument('--cfg4-db', type=int, default=50_000_000, help='configs[4] database size (sharded over the ranks)')
+    ap.add_argument('--cfg4-queries', type=int, default=10_000)
+    ap.add_argument('--no-cfg4', action='store_true')
+    ap.add_argument('--no-allvsall', action='store_true')
     ap.add_argument('--no-search', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--no-fused', action='store_true')

@@ -14,6 +14,7 @@ LIB_PATH = os.environ.get('DCTD_LIB') or os.path.join(_HERE, 'libdctd.so')   # D
 OK = 0
 ERR_ARG, ERR_CUDA, ERR_WORKSPACE, ERR_UNSUPPORTED, ERR_NOMEM = -1, -2, -3, -4, -5
 FP_TABLES_RESIDENT = 1
+L1_HEAP_ONLY = 1
 
 
 class DctdError(RuntimeError):
@@ -81,6 +82,11 @@ def lib():
         'dctd_l1_topk_workspace_bytes': (sz, [i64, i64, i32, i32]),
         'dctd_l1_topk': (C.c_int, [vp, i64, vp, i64, i32, i32, i64, vp, vp, vp, sz, vp]),
         'dctd_l1_topk_merge': (C.c_int, [vp, vp, i32, i64, i32, vp, vp, vp]),
+        'dctd_l1_bound_workspace_bytes': (sz, [i64, i64, i32, i32, i32]),
+        'dctd_l1_bound': (C.c_int, [vp, i64, vp, i64, i32, i32, i32, vp, vp, sz, vp]),
+        'dctd_l1_uses_bound': (C.c_int, [i64, i64, i32, i32]),
+        'dctd_l1_topk_keys': (C.c_int, [vp, i64, vp, i64, i32, i32, i64, vp, vp, vp, sz, u32, vp]),
+        'dctd_l1_keys_merge': (C.c_int, [vp, i32, i64, i32, vp, vp, vp, vp]),
         'dctd_l1_pair_scores': (C.c_int, [vp, i32, vp, vp, vp, i64, vp, vp, vp]),
     }
     hooks = {'dctd_fp_set_variant', 'dctd_fp_set_fusion', 'dctd_fp_timing_read', 'dctd_fp_plan_dump', 'dctd_fp_plan_dump_records',

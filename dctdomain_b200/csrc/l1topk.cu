@@ -25,6 +25,7 @@
 #include <float.h>
 
 #include <algorithm>
+#include <mutex>
 
 #include "dctd_internal.cuh"
 #include "dctd_tma.cuh"
@@ -160,7 +161,8 @@ struct ScanParams {
     unsigned long long *parts;  // [S, nq, k] sorted keys per database split
     int cap;
     // threshold mode (l1_thresh_scan_kernel / l1_thresh_stream_kernel)
-    const unsigned long long *thr_keys;   // [nq, k] sorted keys of the sample: thr = thr_keys[q*k + k-1]
+    const unsigned int *thr_dist;         // [nq] distance bound per query: only vectors with dist <= thr_dist[q] are kept
+                                          // (an upper bound of the true k-th best distance; >= 0x7fffffff = no bound)
     unsigned long long *cand;   // [nq, cmax] candidate keys
     int *cnt;                   // [nq] candidates appended (may exceed cmax: overflow)
     int cmax;
@@ -433,8 +435,8 @@ __global__ void __launch_bounds__(128) l1_sample_min_kernel(const ScanParams p, 
     }
 }
 
-// one CTA per query: k-th smallest of the M minima -> thr_keys[q * k + k - 1] (largest id: ties pass the scan)
-__global__ void __launch_bounds__(256) l1_kth_kernel(const unsigned int *mins, int M, int k, unsigned long long *thr_keys,
+// one CTA per query: k-th smallest of the M minima -> thr_dist[q] (ties at the bound pass the scan)
+__global__ void __launch_bounds__(256) l1_kth_kernel(const unsigned int *mins, int M, int k, unsigned int *thr_dist,
                                                      int *cnt) {
     __shared__ unsigned int v[kMinSlots];
     const long long qi = blockIdx.x;
@@ -456,8 +458,7 @@ __global__ void __launch_bounds__(256) l1_kth_kernel(const unsigned int *mins, i
     }
     if (threadIdx.x == 0) {
         cnt[qi] = 0;                        // candidate counter of the scan that follows
-        const unsigned int dk = (k <= M) ? v[k - 1] : 0xffffffffu;
-        thr_keys[qi * k + k - 1] = (dk == 0xffffffffu) ? kKeyMax : (((unsigned long long)dk << kIdBits) | kIdMask);
+        thr_dist[qi] = (k <= M) ? v[k - 1] : 0xffffffffu;
     }
 }
 
@@ -467,21 +468,28 @@ __global__ void __launch_bounds__(256) l1_kth_kernel(const unsigned int *mins, i
 // the k best overall.  One warp per query; also sets the candidate counter (no memset).
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) l1_seed_kernel(const unsigned long long *thr_keys, long long nq, int k,
-                                                      unsigned long long *cand, int *cnt, int cmax) {
+                                                      unsigned long long *cand, int *cnt, int cmax, bool seed,
+                                                      unsigned int *thr_dist) {
     const int lane = threadIdx.x & 31;
     const long long qi = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (qi >= nq) return;
     int valid = 0;
-    for (int i = lane; i < k; i += 32) {
-        const unsigned long long key = thr_keys[qi * k + i];
-        if (key != kKeyMax) {            // keys are sorted: the valid ones are a prefix
-            cand[qi * cmax + i] = key;
-            ++valid;
+    if (seed) {
+        for (int i = lane; i < k; i += 32) {
+            const unsigned long long key = thr_keys[qi * k + i];
+            if (key != kKeyMax) {            // keys are sorted: the valid ones are a prefix
+                cand[qi * cmax + i] = key;
+                ++valid;
+            }
         }
-    }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) valid += __shfl_xor_sync(0xffffffffu, valid, o);
-    if (lane == 0) cnt[qi] = valid;
+        for (int o = 16; o > 0; o >>= 1) valid += __shfl_xor_sync(0xffffffffu, valid, o);
+    }
+    if (lane == 0) {
+        cnt[qi] = valid;
+        const unsigned long long kth = thr_keys[qi * k + k - 1];
+        thr_dist[qi] = (kth == kKeyMax) ? 0xffffffffu : (unsigned int)(kth >> kIdBits);
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -534,9 +542,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) l1_thresh_scan_kernel(const 
 #pragma unroll
     for (int a = 0; a < TQ; ++a) {
         const long long qi = q0 + warp * TQ + a;
-        unsigned long long th = kKeyMax;
-        if (qi < p.nq) th = p.thr_keys[qi * p.k + p.k - 1];
-        tdist[a] = (qi < p.nq) ? ((th == kKeyMax) ? 0xffffffffu : (unsigned int)(th >> kIdBits)) : 0u;
+        tdist[a] = (qi < p.nq) ? p.thr_dist[qi] : 0u;
     }
     // real group of the tile's first virtual group, kept up without a division per tile: with `skip`, virtual group
     // v = vq * (skip - 1) + vr is real group v + vq + 1
@@ -599,9 +605,7 @@ __global__ void __launch_bounds__(128) l1_thresh_stream_kernel(const ScanParams 
     unsigned int tdist[TQ];
 #pragma unroll
     for (int a = 0; a < TQ; ++a) {
-        unsigned long long th = kKeyMax;
-        if (a < p.nq) th = p.thr_keys[(long long)a * p.k + p.k - 1];
-        tdist[a] = (a < p.nq) ? ((th == kKeyMax) ? 0xffffffffu : (unsigned int)(th >> kIdBits)) : 0u;
+        tdist[a] = (a < p.nq) ? p.thr_dist[a] : 0u;
     }
     constexpr int UC = 6;      // chunks per batch; with PIPE the next batch is requested before the current one is
                                // consumed, across group boundaries too: loads and SADs overlap inside a warp
@@ -676,6 +680,7 @@ struct SelectParams {
     long long nq, id_base;
     float *dist;
     long long *ids;
+    unsigned long long *key_out;   // if set: the result stays packed keys (dist << 40 | id_base + position), kKeyMax padding
     int *qflags;       // out: 1 if the query's list overflowed (its result comes from the heap scan instead)
 };
 
@@ -737,7 +742,9 @@ __global__ void __launch_bounds__(256) l1_select_kernel(const SelectParams p) {
     for (int i = threadIdx.x; i < p.k; i += blockDim.x) {
         const unsigned long long key = (i < K2) ? keys[i] : kKeyMax;
         const long long o = qi * p.k + i;
-        if (key == kKeyMax) {
+        if (p.key_out) {
+            p.key_out[o] = (key == kKeyMax) ? kKeyMax : key + (unsigned long long)p.id_base;
+        } else if (key == kKeyMax) {
             p.dist[o] = FLT_MAX;
             p.ids[o] = -1;
         } else {
@@ -760,7 +767,8 @@ struct MergeParams {
     long long nq;
     int k, cap;                            // cap = power of two >= 2k
     long long id_base;
-    unsigned long long *key_out;           // [grid.y, nq, k] when not the last level (or keys wanted)
+    unsigned long long *key_out;           // [grid.y, nq, k] when not the last level (or keys wanted; with dist/ids set
+                                           // as well, both forms are written)
     float *dist;
     long long *ids;
     const int *qflags;                     // optional: only flagged queries are written
@@ -793,8 +801,11 @@ __global__ void __launch_bounds__(128) l1_merge_kernel(const MergeParams p) {
     __syncwarp();
     if (p.key_out) {
         unsigned long long *out = p.key_out + ((long long)blockIdx.y * p.nq + qi) * p.k;
-        for (int i = lane; i < p.k; i += 32) out[i] = buf[i];
-        return;
+        for (int i = lane; i < p.k; i += 32) {
+            const unsigned long long key = buf[i];
+            out[i] = (key == kKeyMax) ? kKeyMax : key + (unsigned long long)p.id_base;   // id_base: last level only
+        }
+        if (!p.dist) return;
     }
     for (int i = lane; i < p.k; i += 32) {
         const unsigned long long key = buf[i];
@@ -853,12 +864,65 @@ __global__ void pair_scores_kernel(const int8_t *__restrict__ fps, int d, const 
 }
 
 // ------------------------------------------------------------------------------------------
+// bound of a sharded search: the k_local-th best distance of a sample, as int32 (see dctd_l1_bound)
+// ------------------------------------------------------------------------------------------
+__global__ void l1_bound_kernel(const unsigned long long *keys, long long nq, int k, int *bound) {
+    const long long qi = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (qi >= nq) return;
+    const unsigned long long kth = keys[qi * k + k - 1];
+    bound[qi] = (kth == kKeyMax) ? 0x7fffffff : (int)(kth >> kIdBits);
+}
+
+__global__ void l1_fill_kernel(int *p, long long n, int v) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+// ------------------------------------------------------------------------------------------
 // host-side configuration shared by workspace_bytes and topk
 // ------------------------------------------------------------------------------------------
-int g_l1_mode = 0;   // tuning / test hook (dctd_l1_set_mode): 0 = automatic, 1 = force the heap scan, 2 = heap-scan
-                     // thresholds in the streaming regime, 3 = the threshold scan revisits the sampled groups
-constexpr long long kSMs = 148;
-constexpr size_t kSmemLimit = 227 * 1024;
+#ifdef DCTD_TUNING
+int g_l1_mode = 0;   // A/B hook of the tuning build (dctd_l1_set_mode): 2 = heap-scan thresholds in the streaming
+                     // regime, 3 = the threshold scan revisits the sampled groups, 5 = rolled chunk loop
+#else
+constexpr int g_l1_mode = 0;
+#endif
+
+// Limits of the current device (SM count, opt-in shared memory per CTA).  Device properties never change, so the
+// per-device cache below is write-once.
+struct DevInfo {
+    long long sms;
+    size_t smem;
+};
+
+bool dev_info(DevInfo *out) {
+    static std::mutex mu;
+    static DevInfo cache[64];
+    static bool have[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) {
+        out->sms = 148;                       // no device (host-only callers sizing a workspace): B200 figures
+        out->smem = 227 * 1024;
+        cudaGetLastError();
+        return false;
+    }
+    std::lock_guard<std::mutex> lock(mu);
+    if (!have[dev]) {
+        int sms = 0, smem = 0;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+            cudaDeviceGetAttribute(&smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess || sms < 1) {
+            out->sms = 148;
+            out->smem = 227 * 1024;
+            cudaGetLastError();
+            return false;
+        }
+        cache[dev].sms = sms;
+        cache[dev].smem = (size_t)smem;
+        have[dev] = true;
+    }
+    *out = cache[dev];
+    return true;
+}
 
 struct ScanConfig {          // heap scan (l1_scan_kernel)
     int tq, td, stages, cap;
@@ -866,11 +930,11 @@ struct ScanConfig {          // heap scan (l1_scan_kernel)
     size_t smem;
 };
 
-// One CTA per SM is resident (shared memory).  The number of database splits S trades whole waves of 148
+// One CTA per SM is resident (shared memory).  The number of database splits S trades whole waves of `sms`
 // CTAs against per-CTA fixed cost: time(S) ~ waves(S) * (tiles_per_split + overhead_tiles), where
 // overhead_tiles is the warm-up of a CTA expressed in tiles (heap scan: candidate buffers refine often
 // until the thresholds tighten, ~32 tiles' worth; threshold scan: just the query load).
-void pick_splits(long long n_groups, int td, long long n_qtiles, int overhead_tiles, long long *splits,
+void pick_splits(long long sms, long long n_groups, int td, long long n_qtiles, int overhead_tiles, long long *splits,
                  long long *groups_per_split) {
     const long long tiles = std::max<long long>(1, (n_groups + td - 1) / td);
     const long long s_max = std::max<long long>(1, std::min<long long>(1024, tiles / 4));
@@ -879,17 +943,17 @@ void pick_splits(long long n_groups, int td, long long n_qtiles, int overhead_ti
     for (long long sp = 1; sp <= s_max; ++sp) {
         const long long tps = (tiles + sp - 1) / sp;
         const long long real = (tiles + tps - 1) / tps;
-        const long long waves = (real * n_qtiles + kSMs - 1) / kSMs;
+        const long long waves = (real * n_qtiles + sms - 1) / sms;
         const double cost = (double)waves * (double)(tps + overhead_tiles);
         if (cost < best_cost * 0.995) { best_cost = cost; best_s = sp; }
-        if (sp > 4 * kSMs && sp * n_qtiles > 16 * kSMs) break;
+        if (sp > 4 * sms && sp * n_qtiles > 16 * sms) break;
     }
     const long long tiles_per_split = (tiles + best_s - 1) / best_s;
     *groups_per_split = tiles_per_split * td;
     *splits = std::max<long long>(1, (n_groups + *groups_per_split - 1) / *groups_per_split);
 }
 
-bool make_config(long long nq, long long n_groups, int d, int k, ScanConfig *cfg) {
+bool make_config(const DevInfo &di, long long nq, long long n_groups, int d, int k, ScanConfig *cfg) {
     if (k < 1 || k > 992 || d < 1 || d > 2048) return false;
     int cap = 128, tq = 8;
     if (k > 96) { cap = 256; tq = 4; }
@@ -902,14 +966,14 @@ bool make_config(long long nq, long long n_groups, int d, int k, ScanConfig *cfg
         const size_t qt = (size_t)kWarps * tq_;
         return (size_t)128 + qt * dpad + (size_t)st_ * td_ * 32 * dpad + qt * cap * 8 + qt * 12 + 64;
     };
-    if (smem_of(1, td, stages) > kSmemLimit) { td = 1; stages = 2; }      // wide vectors
-    while (tq > 1 && smem_of(tq, td, stages) > kSmemLimit) tq /= 2;
-    if (smem_of(tq, td, stages) > kSmemLimit) return false;
+    if (smem_of(1, td, stages) > di.smem) { td = 1; stages = 2; }      // wide vectors
+    while (tq > 1 && smem_of(tq, td, stages) > di.smem) tq /= 2;
+    if (smem_of(tq, td, stages) > di.smem) return false;
     cfg->tq = tq; cfg->td = td; cfg->stages = stages; cfg->cap = cap;
     cfg->smem = smem_of(tq, td, stages);
     cfg->n_qtiles = (nq + (long long)kWarps * tq - 1) / ((long long)kWarps * tq);
     cfg->n_groups = n_groups;
-    pick_splits(n_groups, td, cfg->n_qtiles, 32, &cfg->splits, &cfg->groups_per_split);
+    pick_splits(di.sms, n_groups, td, cfg->n_qtiles, 32, &cfg->splits, &cfg->groups_per_split);
     return true;
 }
 
@@ -922,12 +986,13 @@ struct ThreshConfig {        // threshold scan (l1_thresh_scan_kernel / l1_thres
 
 struct TopkPlan {
     bool thresh;
+    bool bounded;            // the caller supplies the distance bounds (sharded search): no sample, no seeds
     ScanConfig full;         // heap scan of the whole database: the only scan when !thresh, else the fallback
     ScanConfig samp;         // heap scan of the sample that sets the thresholds
     long long gstride;
     ThreshConfig tc;
     int cmax;
-    size_t off_parts_full, off_parts_samp, off_tmp, off_thr, off_cnt, off_flags, off_cand, off_mins, total;
+    size_t off_parts_full, off_parts_samp, off_tmp, off_thr, off_thrd, off_cnt, off_flags, off_cand, off_mins, total;
     // streaming regime: thresholds from lane minima (l1_sample_min_kernel) instead of a heap scan of the sample
     long long samp_groups;   // sampled groups
     int samp_grid, samp_red, samp_m;   // CTAs of 4 warps, lanes per minimum, minima per query
@@ -935,17 +1000,25 @@ struct TopkPlan {
 
 constexpr int kCmax = 8192;  // candidate slots per query (threshold path)
 constexpr int kMergePPW = 32;
+constexpr long long kThreshMinN = 65536;    // smaller databases: heap scan only
 
-bool make_plan(long long nq, long long n, int d, int k, TopkPlan *pl) {
+// does a database of n vectors take the threshold path (and therefore honour an external bound)?
+bool thresh_eligible(long long n, int k, const ScanConfig &full) {
+    const long long gs = std::min<long long>(32, (kCmax / 4) / std::max(1, k));
+    return n >= kThreshMinN && gs >= 8 && full.td == kTDmax;
+}
+
+bool make_plan(const DevInfo &di, long long nq, long long n, int d, int k, bool bounded, TopkPlan *pl) {
     const long long n_groups = (n + 31) / 32;
-    if (!make_config(nq, n_groups, d, k, &pl->full)) return false;
+    if (!make_config(di, nq, n_groups, d, k, &pl->full)) return false;
     pl->thresh = false;
+    pl->bounded = false;
     pl->cmax = kCmax;
     const int dpad = chunks_of(d) * 16;
     // threshold path: large databases, moderate k (the sample must stay a small fraction of the database
     // while the expected candidate count k * gstride stays well below cmax)
     const long long gs = std::min<long long>(32, (kCmax / 4) / std::max(1, k));
-    if (n >= 65536 && gs >= 8 && pl->full.td == kTDmax) {
+    if (thresh_eligible(n, k, pl->full)) {
         pl->gstride = gs;
         const long long sg = (n_groups + gs - 1) / gs;
         ThreshConfig tc{};
@@ -963,17 +1036,19 @@ bool make_plan(long long nq, long long n, int d, int k, TopkPlan *pl) {
             const size_t qt = (size_t)tc.nw * tc.tq;
             tc.smem = 128 + qt * dpad + (size_t)kStagesMax * kTDmax * 32 * dpad + 64;
             tc.n_qtiles = (nq + (long long)qt - 1) / (long long)qt;
-            // the sampled groups are not scanned again (their top-k seeds the candidate lists)
-            pick_splits(g_l1_mode == 3 ? n_groups : n_groups - sg, kTDmax, tc.n_qtiles, 2, &tc.splits, &tc.groups_per_split);
+            // own thresholds: the sampled groups are not scanned again (their top-k seeds the candidate lists)
+            pick_splits(di.sms, (bounded || g_l1_mode == 3) ? n_groups : n_groups - sg, kTDmax, tc.n_qtiles, 2, &tc.splits,
+                        &tc.groups_per_split);
         }
-        if (tc.smem <= kSmemLimit && make_config(nq, sg, d, k, &pl->samp)) {
+        if (tc.smem <= di.smem && (bounded || make_config(di, nq, sg, d, k, &pl->samp))) {
             pl->tc = tc;
             pl->thresh = true;
+            pl->bounded = bounded;
         }
-        if (pl->thresh && tc.stream) {
+        if (pl->thresh && tc.stream && !bounded) {
             // one warp per sampled group up to 8 CTAs of 4 warps per SM; as many minima per query as fit
             pl->samp_groups = sg;
-            const long long warps = std::min<long long>(sg, kSMs * 8 * 4);
+            const long long warps = std::min<long long>(sg, di.sms * 8 * 4);
             pl->samp_grid = (int)((warps + 3) / 4);
             int red = 1;
             while ((long long)pl->samp_grid * 4 * (32 / red) > kMinSlots && red < 32) red <<= 1;
@@ -986,16 +1061,19 @@ bool make_plan(long long nq, long long n, int d, int k, TopkPlan *pl) {
     const size_t list = (size_t)nq * (size_t)k * 8;
     pl->off_parts_full = take((size_t)pl->full.splits * list);
     size_t tmp_parts = pl->full.splits > kMergePPW ? (size_t)((pl->full.splits + kMergePPW - 1) / kMergePPW) : 0;
-    pl->off_parts_samp = pl->off_thr = pl->off_cnt = pl->off_flags = pl->off_cand = 0;
+    pl->off_parts_samp = pl->off_thr = pl->off_thrd = pl->off_cnt = pl->off_flags = pl->off_cand = pl->off_mins = 0;
     if (pl->thresh) {
-        pl->off_parts_samp = take((size_t)pl->samp.splits * list);
-        if (pl->samp.splits > kMergePPW)
-            tmp_parts = std::max(tmp_parts, (size_t)((pl->samp.splits + kMergePPW - 1) / kMergePPW));
-        pl->off_thr = take(list);
+        if (!pl->bounded) {
+            pl->off_parts_samp = take((size_t)pl->samp.splits * list);
+            if (pl->samp.splits > kMergePPW)
+                tmp_parts = std::max(tmp_parts, (size_t)((pl->samp.splits + kMergePPW - 1) / kMergePPW));
+            pl->off_thr = take(list);
+            pl->off_thrd = take((size_t)nq * sizeof(unsigned int));
+            pl->off_mins = pl->tc.stream ? take((size_t)16 * kMinSlots * sizeof(unsigned int)) : 0;
+        }
         pl->off_cnt = take((size_t)nq * sizeof(int));
         pl->off_flags = take((size_t)nq * sizeof(int));
         pl->off_cand = take((size_t)nq * (size_t)pl->cmax * 8);
-        pl->off_mins = pl->tc.stream ? take((size_t)16 * kMinSlots * sizeof(unsigned int)) : 0;
     }
     pl->off_tmp = take(tmp_parts * list);
     pl->total = off + 256;
@@ -1039,12 +1117,13 @@ int launch_heap(const ScanConfig &c, ScanParams sp, cudaStream_t stream) {
     return DCTD_OK;
 }
 
-// folds `parts` sorted key lists per query; the result goes to (dist, ids) or, if key_out is given, stays keys
+// folds `parts` sorted key lists per query; the result goes to (dist, ids) and / or, if key_out is given, to keys
+// (with id_base added to the position field)
 int run_merge(const unsigned long long *keys, long long parts, long long nq, int k, long long id_base, float *dist,
               long long *ids, unsigned long long *key_out, const int *qflags, unsigned long long *tmp,
               cudaStream_t stream) {
     MergeParams mp{};
-    mp.nq = nq; mp.k = k; mp.cap = next_pow2(2 * k); mp.id_base = id_base; mp.qflags = qflags;
+    mp.nq = nq; mp.k = k; mp.cap = next_pow2(2 * k); mp.qflags = qflags;
     const int warps = 4;
     const size_t msmem = (size_t)warps * mp.cap * 8;
     DCTD_CUDA_TRY(cudaFuncSetAttribute(l1_merge_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem));
@@ -1052,133 +1131,102 @@ int run_merge(const unsigned long long *keys, long long parts, long long nq, int
     if (parts > kMergePPW) {
         if (parts > (long long)kMergePPW * kMergePPW) return DCTD_ERR_UNSUPPORTED;
         const long long chunks = (parts + kMergePPW - 1) / kMergePPW;
-        mp.key_parts = keys; mp.parts = (int)parts; mp.ppw = kMergePPW; mp.key_out = tmp;
+        mp.key_parts = keys; mp.parts = (int)parts; mp.ppw = kMergePPW; mp.key_out = tmp; mp.id_base = 0;
         l1_merge_kernel<false><<<dim3(gx, (unsigned)chunks), warps * 32, msmem, stream>>>(mp);
         DCTD_LAUNCH_CHECK();
         keys = tmp;
         parts = chunks;
     }
-    mp.key_parts = keys; mp.parts = (int)parts; mp.ppw = (int)parts; mp.key_out = key_out;
+    mp.key_parts = keys; mp.parts = (int)parts; mp.ppw = (int)parts; mp.key_out = key_out; mp.id_base = id_base;
     mp.dist = dist; mp.ids = ids;
     l1_merge_kernel<false><<<dim3(gx, 1), warps * 32, msmem, stream>>>(mp);
     DCTD_LAUNCH_CHECK();
     return DCTD_OK;
 }
 
-}  // namespace
-
-extern "C" {
-
-int dctd_l1_set_mode(int mode) { g_l1_mode = mode; return DCTD_OK; }
-
-size_t dctd_l1_packed_bytes(int64_t n, int32_t d) {
-    if (n < 0 || d < 1) return 0;
-    return (size_t)((n + 31) / 32) * 32 * (size_t)chunks_of(d) * 16;
-}
-
-int dctd_l1_pack(const int8_t *d_rows, int64_t n, int32_t d, int64_t n_offset, void *d_packed, void *stream) {
-    if (n < 0 || d < 1 || n_offset < 0 || (n > 0 && (!d_rows || !d_packed))) return DCTD_ERR_ARG;
-    if (n == 0) return DCTD_OK;
-    const long long total = ((n_offset + n + 31) / 32 * 32 - n_offset / 32 * 32) * chunks_of(d);
-    const int block = 256;
-    const int grid = (int)std::min<long long>((total + block - 1) / block, 148 * 16);
-    pack_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(d_rows, n, d, n_offset, (uint4 *)d_packed);
-    DCTD_LAUNCH_CHECK();
-    return DCTD_OK;
-}
-
-int dctd_l1_unpack(const void *d_packed, int64_t n, int32_t d, int8_t *d_rows, void *stream) {
-    if (n < 0 || d < 1 || (n > 0 && (!d_rows || !d_packed))) return DCTD_ERR_ARG;
-    if (n == 0) return DCTD_OK;
-    const long long total = n * chunks_of(d);
-    const int block = 256;
-    const int grid = (int)std::min<long long>((total + block - 1) / block, 148 * 16);
-    unpack_kernel<<<grid, block, 0, (cudaStream_t)stream>>>((const uint4 *)d_packed, n, d, d_rows);
-    DCTD_LAUNCH_CHECK();
-    return DCTD_OK;
-}
-
-size_t dctd_l1_topk_workspace_bytes(int64_t nq, int64_t n, int32_t d, int32_t k) {
-    TopkPlan pl;
-    if (nq <= 0 || n < 0 || !make_plan(nq, n, d, k, &pl)) return 0;
-    return pl.total;
-}
-
-int dctd_l1_topk(const int8_t *d_q, int64_t nq, const void *d_packed, int64_t n, int32_t d, int32_t k,
-                 int64_t id_base, float *d_dist, int64_t *d_ids, void *d_workspace, size_t workspace_bytes,
-                 void *stream_) {
-    if (nq < 0 || n < 0 || k < 1 || d < 1) return DCTD_ERR_ARG;
+// The search proper.  Result as (dist, ids) and / or packed keys.  `bound` (optional, device int32 [nq]): only vectors
+// with distance <= bound[q] need to be reported for query q (the caller knows that the k best over ALL shards lie within).
+int run_topk(const int8_t *d_q, int64_t nq, const void *d_packed, int64_t n, int32_t d, int32_t k, int64_t id_base,
+             const int32_t *d_bound, float *d_dist, long long *ids, unsigned long long *keys_out, void *d_workspace,
+             size_t workspace_bytes, uint32_t flags, cudaStream_t stream) {
+    if (nq < 0 || n < 0 || k < 1 || d < 1 || id_base < 0) return DCTD_ERR_ARG;
     if (nq == 0) return DCTD_OK;
-    if (!d_q || !d_dist || !d_ids || (n > 0 && !d_packed)) return DCTD_ERR_ARG;
-    if (n >= (1LL << kIdBits)) return DCTD_ERR_UNSUPPORTED;
+    if (!d_q || (!keys_out && (!d_dist || !ids)) || (n > 0 && !d_packed)) return DCTD_ERR_ARG;
+    if (n >= (1LL << kIdBits) || id_base + n >= (1LL << kIdBits)) return DCTD_ERR_UNSUPPORTED;
+    DevInfo di;
+    dev_info(&di);
     TopkPlan pl;
-    if (!make_plan(nq, n, d, k, &pl)) return DCTD_ERR_UNSUPPORTED;
-    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!make_plan(di, nq, n, d, k, d_bound != nullptr, &pl)) return DCTD_ERR_UNSUPPORTED;
     if (!d_workspace || workspace_bytes < pl.total) return DCTD_ERR_WORKSPACE;
     if (((uintptr_t)d_workspace & 255) != 0 || ((uintptr_t)d_packed & 15) != 0) return DCTD_ERR_ARG;
     char *ws = (char *)d_workspace;
     unsigned long long *parts_full = (unsigned long long *)(ws + pl.off_parts_full);
     unsigned long long *tmp = (unsigned long long *)(ws + pl.off_tmp);
-    long long *ids = (long long *)d_ids;
 
     if (n == 0) {   // empty database: every slot is padding
         DCTD_CUDA_TRY(cudaMemsetAsync(parts_full, 0xff, (size_t)nq * k * 8, stream));
-        return run_merge(parts_full, 1, nq, k, id_base, d_dist, ids, nullptr, nullptr, tmp, stream);
+        return run_merge(parts_full, 1, nq, k, id_base, d_dist, ids, keys_out, nullptr, tmp, stream);
     }
     ScanParams sp{};
     sp.q = d_q; sp.packed = (const uint4 *)d_packed; sp.nq = nq; sp.n = n; sp.d = d; sp.k = k; sp.gstride = 1;
 
-    if (!pl.thresh || g_l1_mode == 1) {
+    if (!pl.thresh || (flags & DCTD_L1_HEAP_ONLY)) {
         sp.parts = parts_full;
         int rc = launch_heap(pl.full, sp, stream);
         if (rc != DCTD_OK) return rc;
-        return run_merge(parts_full, pl.full.splits, nq, k, id_base, d_dist, ids, nullptr, nullptr, tmp, stream);
+        return run_merge(parts_full, pl.full.splits, nq, k, id_base, d_dist, ids, keys_out, nullptr, tmp, stream);
     }
 
     // ---- threshold path ----
-    unsigned long long *parts_samp = (unsigned long long *)(ws + pl.off_parts_samp);
-    unsigned long long *thr = (unsigned long long *)(ws + pl.off_thr);
     int *cnt = (int *)(ws + pl.off_cnt);
-    int *flags = (int *)(ws + pl.off_flags);
+    int *flagsq = (int *)(ws + pl.off_flags);
     unsigned long long *cand = (unsigned long long *)(ws + pl.off_cand);
-    // 1. thresholds: from lane minima over every gstride-th group (few queries), or the exact top-k of that sample
-    if (pl.tc.stream && g_l1_mode != 2) {
-        ScanParams s1 = sp;
-        s1.gstride = pl.gstride;
-        s1.n_groups = pl.samp_groups;
-        unsigned int *mins = (unsigned int *)(ws + pl.off_mins);
-        typedef void (*MinFn)(const ScanParams, unsigned int *, int);
-        const int tq = pl.tc.tq;
-        MinFn fn = tq == 4 ? l1_sample_min_kernel<4> : (tq == 8 ? l1_sample_min_kernel<8> : l1_sample_min_kernel<16>);
-        // every slot below samp_m is written (lanes that saw no vector write 0xffffffff = "no bound")
-        fn<<<pl.samp_grid, 128, pl.tc.smem, stream>>>(s1, mins, pl.samp_red);
-        DCTD_LAUNCH_CHECK();
-        l1_kth_kernel<<<(unsigned)nq, 256, 0, stream>>>(mins, pl.samp_m, k, thr, cnt);
-        DCTD_LAUNCH_CHECK();
-    } else {
-        ScanParams s1 = sp;
-        s1.parts = parts_samp;
-        s1.gstride = pl.gstride;
-        int rc = launch_heap(pl.samp, s1, stream);
-        if (rc != DCTD_OK) return rc;
-        rc = run_merge(parts_samp, pl.samp.splits, nq, k, 0, nullptr, nullptr, thr, nullptr, tmp, stream);
-        if (rc != DCTD_OK) return rc;
-    }
-    // 2. one pass over the database: append everything within the threshold
-    if (pl.tc.stream) {
-        if (g_l1_mode == 2) DCTD_CUDA_TRY(cudaMemsetAsync(cnt, 0, (size_t)nq * sizeof(int), stream));
-    } else if (g_l1_mode == 3) {
+    const unsigned int *thrd = nullptr;
+    bool skip_sample = false;
+    if (pl.bounded) {
+        // 1'. the caller's bounds; nothing is seeded, every group is scanned
+        thrd = (const unsigned int *)d_bound;
         DCTD_CUDA_TRY(cudaMemsetAsync(cnt, 0, (size_t)nq * sizeof(int), stream));
     } else {
-        l1_seed_kernel<<<(unsigned)((nq + 3) / 4), 128, 0, stream>>>(thr, nq, k, cand, cnt, pl.cmax);
-        DCTD_LAUNCH_CHECK();
+        unsigned long long *parts_samp = (unsigned long long *)(ws + pl.off_parts_samp);
+        unsigned long long *thr = (unsigned long long *)(ws + pl.off_thr);
+        unsigned int *thrw = (unsigned int *)(ws + pl.off_thrd);
+        thrd = thrw;
+        // 1. thresholds: from lane minima over every gstride-th group (few queries), or the exact top-k of that sample
+        if (pl.tc.stream && g_l1_mode != 2) {
+            ScanParams s1 = sp;
+            s1.gstride = pl.gstride;
+            s1.n_groups = pl.samp_groups;
+            unsigned int *mins = (unsigned int *)(ws + pl.off_mins);
+            typedef void (*MinFn)(const ScanParams, unsigned int *, int);
+            const int tq = pl.tc.tq;
+            MinFn fn = tq == 4 ? l1_sample_min_kernel<4> : (tq == 8 ? l1_sample_min_kernel<8> : l1_sample_min_kernel<16>);
+            // every slot below samp_m is written (lanes that saw no vector write 0xffffffff = "no bound")
+            fn<<<pl.samp_grid, 128, pl.tc.smem, stream>>>(s1, mins, pl.samp_red);
+            DCTD_LAUNCH_CHECK();
+            l1_kth_kernel<<<(unsigned)nq, 256, 0, stream>>>(mins, pl.samp_m, k, thrw, cnt);   // also zeroes cnt
+            DCTD_LAUNCH_CHECK();
+        } else {
+            ScanParams s1 = sp;
+            s1.parts = parts_samp;
+            s1.gstride = pl.gstride;
+            int rc = launch_heap(pl.samp, s1, stream);
+            if (rc != DCTD_OK) return rc;
+            rc = run_merge(parts_samp, pl.samp.splits, nq, k, 0, nullptr, nullptr, thr, nullptr, tmp, stream);
+            if (rc != DCTD_OK) return rc;
+            // the sample's top-k seeds the candidate lists (then the scan can leave the sampled groups out)
+            skip_sample = !pl.tc.stream && g_l1_mode != 3;
+            l1_seed_kernel<<<(unsigned)((nq + 3) / 4), 128, 0, stream>>>(thr, nq, k, cand, cnt, pl.cmax, skip_sample, thrw);
+            DCTD_LAUNCH_CHECK();
+        }
     }
+    // 2. one pass over the database: append everything within the bound
     {
         ScanParams s2 = sp;
-        s2.thr_keys = thr; s2.cand = cand; s2.cnt = cnt; s2.cmax = pl.cmax;
+        s2.thr_dist = thrd; s2.cand = cand; s2.cnt = cnt; s2.cmax = pl.cmax;
         s2.n_groups = (n + 31) / 32;
         const ThreshConfig &tc = pl.tc;
-        if (!tc.stream && g_l1_mode != 3) {       // every group but the sampled ones (mode 3: rescan them, for A/B runs)
+        if (skip_sample) {       // every group but the sampled ones
             s2.skip = pl.gstride;
             s2.n_groups -= (s2.n_groups + pl.gstride - 1) / pl.gstride;
         }
@@ -1187,7 +1235,7 @@ int dctd_l1_topk(const int8_t *d_q, int64_t nq, const void *d_packed, int64_t n,
             int per_sm = 0;
             DCTD_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, 128, tc.smem));
             const long long want = std::max<long long>(1, (s2.n_groups + 3) / 4);
-            const int grid = (int)std::min<long long>(want, kSMs * std::max(1, per_sm));
+            const int grid = (int)std::min<long long>(want, di.sms * std::max(1, per_sm));
             fn<<<grid, 128, tc.smem, stream>>>(s2);
             DCTD_LAUNCH_CHECK();
         } else {
@@ -1207,22 +1255,158 @@ int dctd_l1_topk(const int8_t *d_q, int64_t nq, const void *d_packed, int64_t n,
     {
         SelectParams se{};
         se.cand = cand; se.cnt = cnt; se.cmax = pl.cmax; se.k = k; se.nq = nq; se.id_base = id_base;
-        se.dist = d_dist; se.ids = ids; se.qflags = flags;
+        se.dist = d_dist; se.ids = ids; se.key_out = keys_out; se.qflags = flagsq;
         const size_t ssmem = (size_t)pl.cmax * 8;
         DCTD_CUDA_TRY(cudaFuncSetAttribute(l1_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssmem));
         l1_select_kernel<<<(unsigned)nq, 256, ssmem, stream>>>(se);
         DCTD_LAUNCH_CHECK();
     }
-    // 4. flagged queries (candidate list overflow: heavy distance ties, adversarial order) are redone by
-    //    the heap scan; CTAs of unflagged query tiles exit at once, so this costs a few microseconds
+    // 4. flagged queries (candidate list overflow: heavy distance ties, adversarial order, a bound that is not one)
+    //    are redone by the heap scan; CTAs of unflagged query tiles exit at once, so this costs a few microseconds
     {
         ScanParams s4 = sp;
         s4.parts = parts_full;
-        s4.qflags = flags;
+        s4.qflags = flagsq;
         int rc = launch_heap(pl.full, s4, stream);
         if (rc != DCTD_OK) return rc;
-        return run_merge(parts_full, pl.full.splits, nq, k, id_base, d_dist, ids, nullptr, flags, tmp, stream);
+        return run_merge(parts_full, pl.full.splits, nq, k, id_base, keys_out ? nullptr : d_dist, keys_out ? nullptr : ids,
+                         keys_out, flagsq, tmp, stream);
     }
+}
+
+// sample of dctd_l1_bound: every `stride`-th group
+struct BoundPlan {
+    ScanConfig samp;
+    long long stride;
+    size_t off_parts, off_keys, off_tmp, total;
+};
+
+bool make_bound_plan(const DevInfo &di, long long nq, long long n, int d, int k_local, int stride, BoundPlan *bp) {
+    const long long n_groups = (n + 31) / 32;
+    bp->stride = stride > 0 ? stride : 32;
+    const long long sg = (n_groups + bp->stride - 1) / bp->stride;
+    if (!make_config(di, nq, sg, d, k_local, &bp->samp)) return false;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { const size_t o = off; off += dctd::align_up(bytes, 256); return o; };
+    const size_t list = (size_t)nq * (size_t)k_local * 8;
+    bp->off_parts = take((size_t)bp->samp.splits * list);
+    bp->off_keys = take(list);
+    bp->off_tmp = take(bp->samp.splits > kMergePPW ? (size_t)((bp->samp.splits + kMergePPW - 1) / kMergePPW) * list : 0);
+    bp->total = off + 256;
+    return true;
+}
+
+}  // namespace
+
+extern "C" {
+
+#ifdef DCTD_TUNING
+int dctd_l1_set_mode(int mode) { g_l1_mode = mode; return DCTD_OK; }
+#endif
+
+size_t dctd_l1_packed_bytes(int64_t n, int32_t d) {
+    if (n < 0 || d < 1) return 0;
+    return (size_t)((n + 31) / 32) * 32 * (size_t)chunks_of(d) * 16;
+}
+
+int dctd_l1_pack(const int8_t *d_rows, int64_t n, int32_t d, int64_t n_offset, void *d_packed, void *stream) {
+    if (n < 0 || d < 1 || n_offset < 0 || (n > 0 && (!d_rows || !d_packed))) return DCTD_ERR_ARG;
+    if (n == 0) return DCTD_OK;
+    DevInfo di;
+    dev_info(&di);
+    const long long total = ((n_offset + n + 31) / 32 * 32 - n_offset / 32 * 32) * chunks_of(d);
+    const int block = 256;
+    const int grid = (int)std::min<long long>((total + block - 1) / block, di.sms * 16);
+    pack_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(d_rows, n, d, n_offset, (uint4 *)d_packed);
+    DCTD_LAUNCH_CHECK();
+    return DCTD_OK;
+}
+
+int dctd_l1_unpack(const void *d_packed, int64_t n, int32_t d, int8_t *d_rows, void *stream) {
+    if (n < 0 || d < 1 || (n > 0 && (!d_rows || !d_packed))) return DCTD_ERR_ARG;
+    if (n == 0) return DCTD_OK;
+    DevInfo di;
+    dev_info(&di);
+    const long long total = n * chunks_of(d);
+    const int block = 256;
+    const int grid = (int)std::min<long long>((total + block - 1) / block, di.sms * 16);
+    unpack_kernel<<<grid, block, 0, (cudaStream_t)stream>>>((const uint4 *)d_packed, n, d, d_rows);
+    DCTD_LAUNCH_CHECK();
+    return DCTD_OK;
+}
+
+size_t dctd_l1_topk_workspace_bytes(int64_t nq, int64_t n, int32_t d, int32_t k) {
+    DevInfo di;
+    dev_info(&di);
+    TopkPlan a, b;
+    if (nq <= 0 || n < 0 || !make_plan(di, nq, n, d, k, false, &a) || !make_plan(di, nq, n, d, k, true, &b)) return 0;
+    return std::max(a.total, b.total);
+}
+
+int dctd_l1_topk(const int8_t *d_q, int64_t nq, const void *d_packed, int64_t n, int32_t d, int32_t k,
+                 int64_t id_base, float *d_dist, int64_t *d_ids, void *d_workspace, size_t workspace_bytes,
+                 void *stream) {
+    if (nq > 0 && (!d_dist || !d_ids)) return DCTD_ERR_ARG;
+    return run_topk(d_q, nq, d_packed, n, d, k, id_base, nullptr, d_dist, (long long *)d_ids, nullptr, d_workspace,
+                    workspace_bytes, 0u, (cudaStream_t)stream);
+}
+
+int dctd_l1_topk_keys(const int8_t *d_q, int64_t nq, const void *d_packed, int64_t n, int32_t d, int32_t k,
+                      int64_t id_base, const int32_t *d_bound, uint64_t *d_keys, void *d_workspace,
+                      size_t workspace_bytes, uint32_t flags, void *stream) {
+    if (nq > 0 && !d_keys) return DCTD_ERR_ARG;
+    return run_topk(d_q, nq, d_packed, n, d, k, id_base, d_bound, nullptr, nullptr, (unsigned long long *)d_keys,
+                    d_workspace, workspace_bytes, flags, (cudaStream_t)stream);
+}
+
+int dctd_l1_uses_bound(int64_t nq, int64_t n, int32_t d, int32_t k) {
+    DevInfo di;
+    dev_info(&di);
+    TopkPlan pl;
+    if (nq <= 0 || n < 0 || !make_plan(di, nq, n, d, k, true, &pl)) return 0;
+    return pl.thresh ? 1 : 0;
+}
+
+size_t dctd_l1_bound_workspace_bytes(int64_t nq, int64_t n, int32_t d, int32_t k_local, int32_t sample_stride) {
+    DevInfo di;
+    dev_info(&di);
+    BoundPlan bp;
+    if (nq <= 0 || n < 0 || sample_stride < 0 || !make_bound_plan(di, nq, n, d, k_local, sample_stride, &bp)) return 0;
+    return bp.total;
+}
+
+int dctd_l1_bound(const int8_t *d_q, int64_t nq, const void *d_packed, int64_t n, int32_t d, int32_t k_local,
+                  int32_t sample_stride, int32_t *d_bound, void *d_workspace, size_t workspace_bytes, void *stream_) {
+    if (nq < 0 || n < 0 || k_local < 1 || d < 1 || sample_stride < 0) return DCTD_ERR_ARG;
+    if (nq == 0) return DCTD_OK;
+    if (!d_q || !d_bound || (n > 0 && !d_packed)) return DCTD_ERR_ARG;
+    if (n >= (1LL << kIdBits)) return DCTD_ERR_UNSUPPORTED;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (n == 0) {
+        l1_fill_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, stream>>>(d_bound, nq, 0x7fffffff);
+        DCTD_LAUNCH_CHECK();
+        return DCTD_OK;
+    }
+    DevInfo di;
+    dev_info(&di);
+    BoundPlan bp;
+    if (!make_bound_plan(di, nq, n, d, k_local, sample_stride, &bp)) return DCTD_ERR_UNSUPPORTED;
+    if (!d_workspace || workspace_bytes < bp.total) return DCTD_ERR_WORKSPACE;
+    if (((uintptr_t)d_workspace & 255) != 0 || ((uintptr_t)d_packed & 15) != 0) return DCTD_ERR_ARG;
+    char *ws = (char *)d_workspace;
+    unsigned long long *parts = (unsigned long long *)(ws + bp.off_parts);
+    unsigned long long *keys = (unsigned long long *)(ws + bp.off_keys);
+    unsigned long long *tmp = (unsigned long long *)(ws + bp.off_tmp);
+    ScanParams sp{};
+    sp.q = d_q; sp.packed = (const uint4 *)d_packed; sp.nq = nq; sp.n = n; sp.d = d; sp.k = k_local;
+    sp.gstride = bp.stride; sp.parts = parts;
+    int rc = launch_heap(bp.samp, sp, stream);
+    if (rc != DCTD_OK) return rc;
+    rc = run_merge(parts, bp.samp.splits, nq, k_local, 0, nullptr, nullptr, keys, nullptr, tmp, stream);
+    if (rc != DCTD_OK) return rc;
+    l1_bound_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, stream>>>(keys, nq, k_local, d_bound);
+    DCTD_LAUNCH_CHECK();
+    return DCTD_OK;
 }
 
 int dctd_l1_topk_merge(const float *d_dist_parts, const int64_t *d_ids_parts, int32_t parts, int64_t nq,
@@ -1240,6 +1424,15 @@ int dctd_l1_topk_merge(const float *d_dist_parts, const int64_t *d_ids_parts, in
     l1_merge_kernel<true><<<dim3((unsigned)((nq + warps - 1) / warps), 1), warps * 32, msmem, (cudaStream_t)stream>>>(mp);
     DCTD_LAUNCH_CHECK();
     return DCTD_OK;
+}
+
+int dctd_l1_keys_merge(const uint64_t *d_key_parts, int32_t parts, int64_t nq, int32_t k, float *d_dist,
+                       int64_t *d_ids, uint64_t *d_keys, void *stream) {
+    if (parts < 1 || parts > kMergePPW || nq < 0 || k < 1 || k > 1024) return DCTD_ERR_ARG;
+    if (nq == 0) return DCTD_OK;
+    if (!d_key_parts || ((!d_dist || !d_ids) && !d_keys) || ((d_dist == nullptr) != (d_ids == nullptr))) return DCTD_ERR_ARG;
+    return run_merge((const unsigned long long *)d_key_parts, parts, nq, k, 0, d_dist, (long long *)d_ids,
+                     (unsigned long long *)d_keys, nullptr, nullptr, (cudaStream_t)stream);
 }
 
 int dctd_l1_pair_scores(const int8_t *d_fps, int32_t d, const int64_t *d_off, const int32_t *d_pair_a,

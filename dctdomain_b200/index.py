@@ -91,27 +91,30 @@ class IndexFlat:
         self.ntotal += n
 
     def reconstruct_n(self, i0: int = 0, n: int = -1) -> np.ndarray:
-        """Stored vectors as int8 [n, d] (row-major)."""
+        """Stored vectors [i0, i0 + n) as int8 [n, d] (row-major); only the groups that hold them are unpacked."""
         if n < 0:
             n = self.ntotal - i0
-        out = torch.empty((self.ntotal, self.d), dtype=torch.int8, device=self._dev)
-        if self.ntotal:
-            with torch.cuda.device(self._dev):
-                rc = _lib.lib().dctd_l1_unpack(self._packed.data_ptr(), self.ntotal, self.d, out.data_ptr(),
-                                               torch.cuda.current_stream(self._dev).cuda_stream)
-            _lib.check(rc, 'dctd_l1_unpack')
-        return out[i0:i0 + n].cpu().numpy()
+        if i0 < 0 or n < 0 or i0 + n > self.ntotal:
+            raise ValueError(f'range [{i0}, {i0 + n}) outside the index (ntotal = {self.ntotal})')
+        if n == 0:
+            return np.empty((0, self.d), dtype=np.int8)
+        a = i0 // 32 * 32                                    # first vector of the first group touched
+        out = torch.empty((i0 + n - a, self.d), dtype=torch.int8, device=self._dev)
+        group_bytes = int(_lib.lib().dctd_l1_packed_bytes(32, self.d))
+        with torch.cuda.device(self._dev):
+            rc = _lib.lib().dctd_l1_unpack(self._packed.data_ptr() + (a // 32) * group_bytes, i0 + n - a, self.d,
+                                           out.data_ptr(), torch.cuda.current_stream(self._dev).cuda_stream)
+        _lib.check(rc, 'dctd_l1_unpack')
+        return out[i0 - a:].cpu().numpy()
+
+    def reserve(self, n: int):
+        """Room for ``n`` vectors in total (avoids regrowing while a large database is added in pieces)."""
+        self._reserve(int(n))
 
     # -- search ---------------------------------------------------------------------------
     def search_device(self, q: torch.Tensor, k: int, id_base: int = 0):
         """int8 CUDA queries [nq, d] -> (float32 [nq, k], int64 [nq, k]) CUDA tensors, stream ordered."""
-        if self.metric_type != METRIC_L1:
-            raise NotImplementedError('only METRIC_L1 search is implemented (set index.metric_type = METRIC_L1, '
-                                      'as reference src/query_db.py:76 does)')
-        if q.dtype != torch.int8 or q.dim() != 2 or q.shape[1] != self.d or not q.is_cuda:
-            raise ValueError('queries must be an int8 CUDA tensor [nq, d]')
-        if k < 1:
-            raise ValueError('k must be >= 1')
+        self._check_queries(q, k)
         L = _lib.lib()
         q = q.contiguous()
         nq = int(q.shape[0])
@@ -131,11 +134,96 @@ class IndexFlat:
                 _lib.check(rc, 'dctd_l1_topk')
         return dist, ids
 
+    # -- pieces of a sharded search (dctdomain_b200.sharded; C ABI: dctd_l1_bound / dctd_l1_topk_keys) ---------------
+    def _check_queries(self, q, k):
+        if self.metric_type != METRIC_L1:
+            raise NotImplementedError('only METRIC_L1 search is implemented (set index.metric_type = METRIC_L1, '
+                                      'as reference src/query_db.py:76 does)')
+        if q.dtype != torch.int8 or q.dim() != 2 or q.shape[1] != self.d or not q.is_cuda:
+            raise ValueError('queries must be an int8 CUDA tensor [nq, d]')
+        if k < 1:
+            raise ValueError('k must be >= 1')
+
+    def uses_bound(self, nq: int, n: int, k: int) -> bool:
+        """Would a shard of ``n`` vectors honour an external distance bound for this (nq, k)?"""
+        return bool(_lib.lib().dctd_l1_uses_bound(nq, n, self.d, k))
+
+    def bound_device(self, q: torch.Tensor, k_local: int, sample_stride: int = 0) -> torch.Tensor:
+        """int32 [nq]: upper bound of this shard's k_local-th best distance per query (INT32_MAX = none)."""
+        self._check_queries(q, k_local)
+        L = _lib.lib()
+        q = q.contiguous()
+        nq = int(q.shape[0])
+        out = torch.empty(nq, dtype=torch.int32, device=self._dev)
+        if nq == 0:
+            return out
+        packed_ptr = self._packed.data_ptr() if self._packed is not None else 0
+        with torch.cuda.device(self._dev):
+            stream = torch.cuda.current_stream(self._dev).cuda_stream
+            for b in range(0, nq, _QUERY_BATCH):
+                e = min(nq, b + _QUERY_BATCH)
+                need = int(L.dctd_l1_bound_workspace_bytes(e - b, self.ntotal, self.d, k_local, sample_stride))
+                if need == 0:
+                    raise _lib.DctdError(_lib.ERR_UNSUPPORTED, f'k={k_local}, d={self.d} not supported (k <= 992, d <= 2048)')
+                ws = _workspace(self._dev, need)
+                rc = L.dctd_l1_bound(q[b:e].data_ptr(), e - b, packed_ptr, self.ntotal, self.d, k_local, sample_stride,
+                                     out[b:e].data_ptr(), ws.data_ptr(), ws.numel(), stream)
+                _lib.check(rc, 'dctd_l1_bound')
+        return out
+
+    def search_keys_device(self, q: torch.Tensor, k: int, id_base: int = 0, bound: torch.Tensor = None,
+                           heap_only: bool = False) -> torch.Tensor:
+        """int64 [nq, k] holding the packed keys (distance << 40 | id_base + position, ascending; -1 = empty slot) of this
+        shard's k best among the vectors within ``bound`` (int32 [nq] CUDA tensor; None = no external bound)."""
+        self._check_queries(q, k)
+        L = _lib.lib()
+        q = q.contiguous()
+        nq = int(q.shape[0])
+        keys = torch.empty((nq, k), dtype=torch.int64, device=self._dev)
+        if bound is not None:
+            if bound.dtype != torch.int32 or bound.shape != (nq,) or not bound.is_cuda:
+                raise ValueError('bound must be an int32 CUDA tensor [nq]')
+            bound = bound.contiguous()
+        packed_ptr = self._packed.data_ptr() if self._packed is not None else 0
+        with torch.cuda.device(self._dev):
+            stream = torch.cuda.current_stream(self._dev).cuda_stream
+            for b in range(0, nq, _QUERY_BATCH):
+                e = min(nq, b + _QUERY_BATCH)
+                need = int(L.dctd_l1_topk_workspace_bytes(e - b, self.ntotal, self.d, k))
+                if need == 0:
+                    raise _lib.DctdError(_lib.ERR_UNSUPPORTED, f'k={k}, d={self.d} not supported (k <= 992, d <= 2048)')
+                ws = _workspace(self._dev, need)
+                rc = L.dctd_l1_topk_keys(q[b:e].data_ptr(), e - b, packed_ptr, self.ntotal, self.d, k, id_base,
+                                         bound[b:e].data_ptr() if bound is not None else 0, keys[b:e].data_ptr(),
+                                         ws.data_ptr(), ws.numel(), _lib.L1_HEAP_ONLY if heap_only else 0, stream)
+                _lib.check(rc, 'dctd_l1_topk_keys')
+        return keys
+
     def search(self, x, k: int):
         """faiss-style ``D, I = index.search(x, k)`` with host arrays."""
         q = torch.from_numpy(_as_int8(x, self.d)).to(self._dev)
         dist, ids = self.search_device(q, int(k))
         return dist.cpu().numpy(), ids.cpu().numpy()
+
+
+def keys_merge(key_parts: torch.Tensor, want_keys: bool = False):
+    """int64 [parts, nq, k] packed keys (each list ascending, -1 = empty) -> faiss' (float32 [nq, k], int64 [nq, k]),
+    or the merged keys [nq, k] with ``want_keys`` (CUDA kernel dctd_l1_keys_merge)."""
+    parts, nq, k = key_parts.shape
+    dev = key_parts.device
+    key_parts = key_parts.contiguous()
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        if want_keys:
+            out = torch.empty((nq, k), dtype=torch.int64, device=dev)
+            rc = _lib.lib().dctd_l1_keys_merge(key_parts.data_ptr(), parts, nq, k, 0, 0, out.data_ptr(), stream)
+            _lib.check(rc, 'dctd_l1_keys_merge')
+            return out
+        out_d = torch.empty((nq, k), dtype=torch.float32, device=dev)
+        out_i = torch.empty((nq, k), dtype=torch.int64, device=dev)
+        rc = _lib.lib().dctd_l1_keys_merge(key_parts.data_ptr(), parts, nq, k, out_d.data_ptr(), out_i.data_ptr(), 0, stream)
+    _lib.check(rc, 'dctd_l1_keys_merge')
+    return out_d, out_i
 
 
 class IndexFlatL2(IndexFlat):

@@ -151,6 +151,35 @@ size_t dctd_l1_topk_workspace_bytes(int64_t nq, int64_t n, int32_t d, int32_t k)
 int dctd_l1_topk(const int8_t *d_q, int64_t nq, const void *d_packed, int64_t n, int32_t d,
                  int32_t k, int64_t id_base, float *d_dist, int64_t *d_ids, void *d_workspace,
                  size_t workspace_bytes, void *stream);
+/* ---- sharded databases (one shard per GPU / process; reference call site src/query_db.py:75-76,87 on a database too
+ * large for one device).  Results travel between ranks as packed 64-bit keys: distance << 40 | global position,
+ * ascending = (distance, position) order, UINT64_MAX = empty slot - 8 bytes per entry, one exchange.
+ *
+ *   1. dctd_l1_bound        per query an upper bound of this shard's k_local-th best distance, from a sample of the
+ *                           shard (every sample_stride-th group of 32 vectors; 0 = 32).  INT32_MAX = no bound.
+ *                           With g shards and k_local = ceil(k / g), the maximum over the shards of these bounds is an
+ *                           upper bound of the k-th best distance over the whole database (at least k_local sampled
+ *                           vectors of every shard lie within it): one MAX all-reduce of nq int32.
+ *   2. dctd_l1_topk_keys    this shard's k best among the vectors with distance <= d_bound[q] (d_bound NULL: the
+ *                           function finds its own bound), as keys with id_base added to the positions.
+ *   3. all-gather / all-to-all of the keys, then dctd_l1_keys_merge -> faiss' (float32 distance, int64 id) result. */
+#define DCTD_L1_HEAP_ONLY 1u /* flags of dctd_l1_topk_keys: skip the threshold path (exact heap scan of everything) */
+size_t dctd_l1_bound_workspace_bytes(int64_t nq, int64_t n, int32_t d, int32_t k_local, int32_t sample_stride);
+int dctd_l1_bound(const int8_t *d_q, int64_t nq, const void *d_packed, int64_t n, int32_t d, int32_t k_local,
+                  int32_t sample_stride, int32_t *d_bound, void *d_workspace, size_t workspace_bytes, void *stream);
+/* 1 if dctd_l1_topk_keys would honour an external bound for this problem size (large shard, moderate k); otherwise the
+ * bound exchange can be skipped (the result is the same either way) */
+int dctd_l1_uses_bound(int64_t nq, int64_t n, int32_t d, int32_t k);
+/* workspace: dctd_l1_topk_workspace_bytes(nq, n, d, k) */
+int dctd_l1_topk_keys(const int8_t *d_q, int64_t nq, const void *d_packed, int64_t n, int32_t d, int32_t k,
+                      int64_t id_base, const int32_t *d_bound, uint64_t *d_keys, void *d_workspace,
+                      size_t workspace_bytes, uint32_t flags, void *stream);
+/* d_key_parts uint64 [parts, nq, k] (parts <= 32), each list ascending -> the k smallest keys per query as
+ * (d_dist float32 [nq, k], d_ids int64 [nq, k]) with (FLT_MAX, -1) padding and / or as keys (d_keys, may be NULL;
+ * d_dist and d_ids may both be NULL when d_keys is given) */
+int dctd_l1_keys_merge(const uint64_t *d_key_parts, int32_t parts, int64_t nq, int32_t k, float *d_dist,
+                       int64_t *d_ids, uint64_t *d_keys, void *stream);
+
 /* k-way merge of `parts` sorted lists: d_dist_parts float32 [parts, nq, k], d_ids_parts int64
  * [parts, nq, k] (each ascending by (dist, id), padded with (FLT_MAX, -1)) -> [nq, k].
  * Used after the NCCL all-gather of the per-rank results of a sharded database. */

@@ -258,16 +258,15 @@ def test_streaming_thresholds_on_sorted_database_with_ragged_tail(order):
 
 
 def test_threshold_and_heap_paths_agree_at_scale():
-    from dctdomain_b200 import _lib
+    import torch
+    from dctdomain_b200 import index as dindex
     db = synth.fingerprints(53, 400_000)
     idx = _index(db)
     q = db[::4001][:100]
     a = idx.search(q, 50)
-    _lib.lib().dctd_l1_set_mode(1)
-    try:
-        b = idx.search(q, 50)
-    finally:
-        _lib.lib().dctd_l1_set_mode(0)
+    # the same search forced onto the heap scan (flag DCTD_L1_HEAP_ONLY of dctd_l1_topk_keys), returned as packed keys
+    keys = idx.search_keys_device(torch.from_numpy(q).cuda(), 50, heap_only=True)
+    b = [t.cpu().numpy() for t in dindex.keys_merge(keys.view(1, len(q), 50))]
     assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
     a = idx.search(q[:9], 50)
     assert np.array_equal(a[0], b[0][:9]) and np.array_equal(a[1], b[1][:9])

@@ -1,6 +1,7 @@
-"""world_size-2 gloo test (CPU) of the sharded search plumbing: contiguous shard bounds, id_base, the
-all-gather layout and the merge order.  The per-rank search and the merge kernel are CUDA in the product;
-here the oracle stands in for them (injected), so only the host-side N>1 logic is under test."""
+"""world_size-2/3 gloo tests (CPU) of the sharded search plumbing: contiguous shard bounds, id_base, the bound
+all-reduce, the all-gather / all-to-all layouts and the merge order.  The per-rank steps are CUDA in the product;
+here the oracle stands in for them (tests/oracle_shard.py, injected), so only the host-side N>1 logic is under
+test.  The CUDA + NCCL path itself is compared with the oracle in tests/test_sharded_nccl_gpu.py."""
 import os
 import socket
 
@@ -21,54 +22,59 @@ def _free_port():
     return port
 
 
-def _worker(rank, world, port, out_dir):
+def _database():
+    db = synth.fingerprints(4, 3001)
+    db[1500:1520] = db[2]          # ties that straddle the shard boundary
+    db[2990:3001] = db[7]          # ... and sit at the very end of the last shard
+    return db
+
+
+def _worker(rank, world, port, out_dir, min_bound_rows):
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     sys.path[:0] = [root, os.path.join(root, 'tests')]
-    from dctdomain_b200.sharded import ShardedIndex
-    from oracle import search_oracle as so
+    from dctdomain_b200.sharded import ShardedIndex, shard_bounds
+    from oracle_shard import OracleShard
     os.environ['MASTER_ADDR'] = '127.0.0.1'
     os.environ['MASTER_PORT'] = str(port)
     dist.init_process_group('gloo', rank=rank, world_size=world)
-    db = synth.fingerprints(4, 3001)
-    db[1500:1520] = db[2]          # ties that straddle the shard boundary
-    q = db[:25]
+    db = _database()
     k = 50
-
-    def local_search(qt, kk, id_base):
-        b, e = sh.begin, sh.end
-        d, i = so.l1_topk(qt.numpy(), db[b:e], kk)
-        i = np.where(i >= 0, i + id_base, -1)
-        return torch.from_numpy(d), torch.from_numpy(i)
-
-    def merge(dp, ip):
-        parts, nq, kk = dp.shape
-        d = dp.permute(1, 0, 2).reshape(nq, parts * kk).numpy()
-        i = ip.permute(1, 0, 2).reshape(nq, parts * kk).numpy()
-        od, oi = np.empty((nq, kk), np.float32), np.empty((nq, kk), np.int64)
-        for r in range(nq):
-            key = np.lexsort((np.where(i[r] < 0, np.iinfo(np.int64).max, i[r]), d[r]))[:kk]
-            od[r], oi[r] = d[r][key], i[r][key]
-        return torch.from_numpy(od), torch.from_numpy(oi)
-
-    sh = ShardedIndex(480, len(db), local_search=local_search, merge=merge)
-    assert (sh.begin, sh.end) == ((0, 1500) if rank == 0 else (1500, 3001))
-    d, i = sh.search(torch.from_numpy(q), k)
-    np.savez(os.path.join(out_dir, f'r{rank}.npz'), d=d.numpy(), i=i.numpy())
+    sh = ShardedIndex(480, len(db), shard=OracleShard(480, min_bound_rows=min_bound_rows))
+    assert (sh.begin, sh.end) == shard_bounds(len(db), world, rank)
+    sh.add_local(db[sh.begin:sh.end])
+    out = {}
+    for name, nq in (('few', 7), ('many', 45)):
+        d, i = sh.search(db[:nq], k)                       # host arrays in, host arrays out
+        out[name + '_d'], out[name + '_i'], out[name + '_path'] = d, i, sh.last_path
+    d, i, qb, qe = sh.search_slice(torch.from_numpy(db[:45]), k)
+    out.update(slice_d=d, slice_i=i, slice_b=qb, slice_e=qe, slice_path=sh.last_path)
+    np.savez(os.path.join(out_dir, f'r{rank}.npz'), **out)
     dist.barrier()
     dist.destroy_process_group()
 
 
-def test_two_rank_sharded_search_equals_single(tmp_path):
+@pytest.mark.parametrize('world,min_bound_rows', [(2, 65536), (2, 512), (3, 512)])
+def test_sharded_search_equals_single(tmp_path, world, min_bound_rows):
+    """all_gather path, bound exchange (forced on for tiny shards by min_bound_rows=512) and all_to_all slices against
+    the oracle over the whole database."""
     from oracle import search_oracle as so
-    world = 2
-    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
-    db = synth.fingerprints(4, 3001)
-    db[1500:1520] = db[2]
-    dm, im = so.l1_topk(db[:25], db, 50)
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path), min_bound_rows), nprocs=world, join=True)
+    db = _database()
+    dm, im = so.l1_topk(db[:45], db, 50)
+    bounded = min_bound_rows <= len(db) // world
+    covered = np.zeros(45, bool)
     for r in range(world):
         z = np.load(tmp_path / f'r{r}.npz')
-        assert np.array_equal(z['i'], im) and np.array_equal(z['d'], dm)
+        assert np.array_equal(z['few_i'], im[:7]) and np.array_equal(z['few_d'], dm[:7])
+        assert np.array_equal(z['many_i'], im) and np.array_equal(z['many_d'], dm)
+        assert str(z['few_path']) == 'all_gather'                                   # <= 16 queries: no bound exchange
+        assert str(z['many_path']) == ('bound+all_gather' if bounded else 'all_gather')
+        assert str(z['slice_path']) == ('bound+all_to_all' if bounded else 'all_to_all')
+        qb, qe = int(z['slice_b']), int(z['slice_e'])
+        assert np.array_equal(z['slice_i'], im[qb:qe]) and np.array_equal(z['slice_d'], dm[qb:qe])
+        covered[qb:qe] = True
+    assert covered.all()
 
 
 def test_shard_bounds_cover_everything():
