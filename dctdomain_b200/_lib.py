@@ -77,6 +77,7 @@ def lib():
         'dctd_idct_quant_f64': (C.c_int, [vp, i32, i32, i32, vp, vp]),
         'dctd_l1_packed_bytes': (sz, [i64, i32]),
         'dctd_l1_set_mode': (C.c_int, [C.c_int]),
+        'dctd_l1_stream_stamps': (C.c_int, [vp, i64, i64, i32, i32, vp]),
         'dctd_l1_pack': (C.c_int, [vp, i64, i32, i64, vp, vp]),
         'dctd_l1_unpack': (C.c_int, [vp, i64, i32, vp, vp]),
         'dctd_l1_topk_workspace_bytes': (sz, [i64, i64, i32, i32]),
@@ -90,7 +91,7 @@ def lib():
         'dctd_l1_pair_scores': (C.c_int, [vp, i32, vp, vp, vp, i64, vp, vp, vp]),
     }
     hooks = {'dctd_fp_set_variant', 'dctd_fp_set_fusion', 'dctd_fp_timing_read', 'dctd_fp_plan_dump', 'dctd_fp_plan_dump_records',
-             'dctd_l1_set_mode'}
+             'dctd_l1_set_mode', 'dctd_l1_stream_stamps'}
     for name, (res, args) in sig.items():
         try:
             fn = getattr(L, name)      # AttributeError here = header / library mismatch

@@ -684,50 +684,41 @@ struct SelectParams {
     int *qflags;       // out: 1 if the query's list overflowed (its result comes from the heap scan instead)
 };
 
-__global__ void __launch_bounds__(256) l1_select_kernel(const SelectParams p) {
-    extern __shared__ __align__(16) unsigned long long keys[];
-    const long long qi = blockIdx.x;
-    const int m = p.cnt[qi];
-    if (m > p.cmax) {
-        if (threadIdx.x == 0) p.qflags[qi] = 1;
-        return;
-    }
-    if (threadIdx.x == 0) p.qflags[qi] = 0;
-    int P = 64;
-    while (P < m) P <<= 1;
-    for (int i = threadIdx.x; i < P; i += blockDim.x) keys[i] = (i < m) ? p.cand[qi * p.cmax + i] : kKeyMax;
-    __syncthreads();
-    // Only the k smallest are wanted: bitonic-sort blocks of K2 = 2^ceil(log2 k) keys (alternating directions), then
-    // fold pairs of blocks - the element-wise minimum of an ascending and a descending block holds the K2 smallest of
-    // both as a bitonic sequence, log2(K2) merge steps sort it again - until one ascending block is left.  ~14 P
-    // compare-exchanges instead of the ~33 P of a full sort of P = 2048 keys (the kernel is shared-memory bound).
+// Leaves the K2 = min(P, 2^ceil(log2 k)) smallest of the P keys (P a power of two >= 64) in keys[0..K2), ascending.
+// Called by `nthr` threads that `sync()` joins (a whole CTA, or the consumer warps of the fused streaming kernel).
+// Only the k smallest are wanted: bitonic-sort blocks of K2 keys (alternating directions), then fold pairs of
+// blocks - the element-wise minimum of an ascending and a descending block holds the K2 smallest of both as a
+// bitonic sequence, log2(K2) merge steps sort it again - until one ascending block is left.  ~14 P
+// compare-exchanges instead of the ~33 P of a full sort of P = 2048 keys (the step is shared-memory bound).
+template <typename Sync>
+__device__ __forceinline__ int select_smallest(unsigned long long *keys, int P, int k, int tid, int nthr, Sync sync) {
     int K2 = 2;
-    while (K2 < p.k) K2 <<= 1;
+    while (K2 < k) K2 <<= 1;
     if (K2 > P) K2 = P;
     for (int k2 = 2; k2 <= K2; k2 <<= 1) {
         for (int j = k2 >> 1; j > 0; j >>= 1) {
-            for (int i = threadIdx.x; i < (P >> 1); i += blockDim.x) {
+            for (int i = tid; i < (P >> 1); i += nthr) {
                 const int lo = ((i & ~(j - 1)) << 1) | (i & (j - 1));
                 const int hi = lo | j;
                 const bool up = (lo & k2) == 0;
                 const unsigned long long a = keys[lo], b = keys[hi];
                 if ((a > b) == up) { keys[lo] = b; keys[hi] = a; }
             }
-            __syncthreads();
+            sync();
         }
     }
     // blocks live at multiples of `span`; block c (c-th survivor) is ascending for even c, descending for odd c
     for (int span = K2; span < P; span <<= 1) {
         const int nres = P / (2 * span);                        // surviving blocks after this round
-        for (int i = threadIdx.x; i < nres * K2; i += blockDim.x) {
+        for (int i = tid; i < nres * K2; i += nthr) {
             const int c = i / K2, t = i % K2;
             unsigned long long *A = keys + (size_t)c * 2 * span;
             const unsigned long long a = A[t], b = A[span + t];
             A[t] = a < b ? a : b;
         }
-        __syncthreads();
+        sync();
         for (int j = K2 >> 1; j > 0; j >>= 1) {
-            for (int i = threadIdx.x; i < nres * (K2 >> 1); i += blockDim.x) {
+            for (int i = tid; i < nres * (K2 >> 1); i += nthr) {
                 const int c = i / (K2 >> 1), e = i % (K2 >> 1);
                 unsigned long long *A = keys + (size_t)c * 2 * span;
                 const int lo = ((e & ~(j - 1)) << 1) | (e & (j - 1));
@@ -736,10 +727,28 @@ __global__ void __launch_bounds__(256) l1_select_kernel(const SelectParams p) {
                 const unsigned long long a = A[lo], b = A[hi];
                 if ((a > b) == up) { A[lo] = b; A[hi] = a; }
             }
-            __syncthreads();
+            sync();
         }
     }
-    for (int i = threadIdx.x; i < p.k; i += blockDim.x) {
+    return K2;
+}
+
+// query qi's candidate list -> its k best (faiss' output or packed keys); lists that overflowed are flagged instead
+template <typename Sync>
+__device__ __forceinline__ void select_query(const SelectParams &p, long long qi, unsigned long long *keys, int tid,
+                                             int nthr, Sync sync) {
+    const int m = __ldcg(&p.cnt[qi]);
+    if (m > p.cmax) {
+        if (tid == 0) p.qflags[qi] = 1;
+        return;
+    }
+    if (tid == 0) p.qflags[qi] = 0;
+    int P = 64;
+    while (P < m) P <<= 1;
+    for (int i = tid; i < P; i += nthr) keys[i] = (i < m) ? __ldcg(&p.cand[qi * p.cmax + i]) : kKeyMax;
+    sync();
+    const int K2 = select_smallest(keys, P, p.k, tid, nthr, sync);
+    for (int i = tid; i < p.k; i += nthr) {
         const unsigned long long key = (i < K2) ? keys[i] : kKeyMax;
         const long long o = qi * p.k + i;
         if (p.key_out) {
@@ -753,6 +762,13 @@ __global__ void __launch_bounds__(256) l1_select_kernel(const SelectParams p) {
         }
     }
 }
+
+__global__ void __launch_bounds__(256) l1_select_kernel(const SelectParams p) {
+    extern __shared__ __align__(16) unsigned long long keys[];
+    select_query(p, blockIdx.x, keys, threadIdx.x, blockDim.x, [] { __syncthreads(); });
+}
+
+#include "l1_stream.cuh"
 
 // ------------------------------------------------------------------------------------------
 // merge kernel: sorted lists of k keys per (part, query) -> k best.  One warp per (query, chunk of
@@ -882,6 +898,7 @@ __global__ void l1_fill_kernel(int *p, long long n, int v) {
 // host-side configuration shared by workspace_bytes and topk
 // ------------------------------------------------------------------------------------------
 #ifdef DCTD_TUNING
+int g_l1_var = 0;
 int g_l1_mode = 0;   // A/B hook of the tuning build (dctd_l1_set_mode): 2 = heap-scan thresholds in the streaming
                      // regime, 3 = the threshold scan revisits the sampled groups, 5 = rolled chunk loop
 #else
@@ -893,6 +910,7 @@ constexpr int g_l1_mode = 0;
 struct DevInfo {
     long long sms;
     size_t smem;
+    bool coop;       // cooperative launches (grid-wide barriers) supported
 };
 
 bool dev_info(DevInfo *out) {
@@ -903,26 +921,34 @@ bool dev_info(DevInfo *out) {
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) {
         out->sms = 148;                       // no device (host-only callers sizing a workspace): B200 figures
         out->smem = 227 * 1024;
+        out->coop = true;
         cudaGetLastError();
         return false;
     }
     std::lock_guard<std::mutex> lock(mu);
     if (!have[dev]) {
-        int sms = 0, smem = 0;
+        int sms = 0, smem = 0, coop = 0;
         if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
-            cudaDeviceGetAttribute(&smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess || sms < 1) {
+            cudaDeviceGetAttribute(&smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess ||
+            cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev) != cudaSuccess || sms < 1) {
             out->sms = 148;
             out->smem = 227 * 1024;
+            out->coop = true;
             cudaGetLastError();
             return false;
         }
         cache[dev].sms = sms;
         cache[dev].smem = (size_t)smem;
+        cache[dev].coop = coop != 0;
         have[dev] = true;
     }
     *out = cache[dev];
     return true;
 }
+
+constexpr int kCmax = 8192;  // candidate slots per query (threshold path)
+constexpr size_t kCmaxBytes = (size_t)kCmax * 8;
+constexpr int kMergePPW = 32;
 
 struct ScanConfig {          // heap scan (l1_scan_kernel)
     int tq, td, stages, cap;
@@ -984,6 +1010,51 @@ struct ThreshConfig {        // threshold scan (l1_thresh_scan_kernel / l1_thres
     size_t smem;
 };
 
+struct StreamCfg {           // fused streaming kernel (l1_stream_fused_kernel)
+    bool ok;
+    int tq, nw, td, nh, stages, kscr_n;      // queries per pass, consumer warps, groups per turn, parts per group, ring slots
+    size_t smem;
+};
+
+// ring of as many group-sized stages as fit next to the queries and the k-th scratch; the consumers hold nw * td of
+// them, the rest is in flight
+StreamCfg stream_cfg(const DevInfo &di, long long nq, int d) {
+    StreamCfg c{};
+    c.tq = nq <= 4 ? 4 : (nq <= 8 ? 8 : (nq <= 12 ? 12 : 16));
+    c.nw = 7;                // d = 480: 14 group slots, every warp owns two
+    c.td = 1;
+    c.nh = 1;
+#ifdef DCTD_TUNING
+    g_l1_var = 0;
+    if (g_l1_mode == 6) { c.nw = 4; c.td = 2; }
+    if (g_l1_mode == 7) { c.nw = 5; c.td = 2; }
+    if (g_l1_mode == 8) { c.nw = 6; c.td = 2; }
+    if (g_l1_mode == 16) { c.nw = 4; c.td = 2; g_l1_var = 1; }
+    if (g_l1_mode == 17) { c.nw = 5; c.td = 2; g_l1_var = 1; }
+    if (g_l1_mode == 26) { c.nw = 4; c.td = 2; g_l1_var = 2; }
+    if (g_l1_mode == 27) { c.nw = 5; c.td = 2; g_l1_var = 2; }
+#endif
+    const size_t dpad = (size_t)chunks_of(d) * 16, pbytes = 32 * dpad / c.nh;
+    for (;;) {
+        c.kscr_n = (int)((std::min<long long>(di.sms * c.nw, kMinSlots) + 31) / 32 * 32);   // minima per query
+        const size_t fixed = kStreamHeader + (size_t)c.tq * dpad + (size_t)c.kscr_n * sizeof(unsigned int);
+        const size_t avail = di.smem - 1024;          // room for the kernel's static shared memory
+        if (avail <= fixed) return c;
+        const long long st = std::min<long long>(kStreamMaxSlots, (long long)((avail - fixed) / pbytes));
+        const long long per_round = (long long)c.nw * c.td * c.nh;
+        if (st < per_round + c.td * c.nh && c.nw > 1) {                     // wide vectors: fewer consumers
+            c.nw = c.nw > 4 ? 4 : c.nw / 2;
+            continue;
+        }
+        // the ring is also the buffer of the final selection: cmax candidates + kFastSortCap compacted keys
+        if (st < per_round || kCmaxBytes + (size_t)kFastSortCap * 8 > (size_t)st * pbytes) return c;
+        c.stages = (int)(st >= 2 * per_round ? st / per_round * per_round : st);   // whole rounds: fixed slot owners
+        c.smem = fixed + (size_t)c.stages * pbytes;
+        c.ok = di.coop;
+        return c;
+    }
+}
+
 struct TopkPlan {
     bool thresh;
     bool bounded;            // the caller supplies the distance bounds (sharded search): no sample, no seeds
@@ -991,15 +1062,15 @@ struct TopkPlan {
     ScanConfig samp;         // heap scan of the sample that sets the thresholds
     long long gstride;
     ThreshConfig tc;
+    StreamCfg fused;         // tc.stream: the one-launch streaming kernel, when its ring fits
     int cmax;
-    size_t off_parts_full, off_parts_samp, off_tmp, off_thr, off_thrd, off_cnt, off_flags, off_cand, off_mins, total;
+    size_t off_parts_full, off_parts_samp, off_tmp, off_thr, off_thrd, off_ctl, off_cnt, off_flags, off_cand, off_mins, total;
     // streaming regime: thresholds from lane minima (l1_sample_min_kernel) instead of a heap scan of the sample
     long long samp_groups;   // sampled groups
     int samp_grid, samp_red, samp_m;   // CTAs of 4 warps, lanes per minimum, minima per query
 };
 
-constexpr int kCmax = 8192;  // candidate slots per query (threshold path)
-constexpr int kMergePPW = 32;
+
 constexpr long long kThreshMinN = 65536;    // smaller databases: heap scan only
 
 // does a database of n vectors take the threshold path (and therefore honour an external bound)?
@@ -1013,6 +1084,7 @@ bool make_plan(const DevInfo &di, long long nq, long long n, int d, int k, bool 
     if (!make_config(di, nq, n_groups, d, k, &pl->full)) return false;
     pl->thresh = false;
     pl->bounded = false;
+    pl->fused = StreamCfg{};
     pl->cmax = kCmax;
     const int dpad = chunks_of(d) * 16;
     // threshold path: large databases, moderate k (the sample must stay a small fraction of the database
@@ -1028,6 +1100,7 @@ bool make_plan(const DevInfo &di, long long nq, long long n, int d, int k, bool 
             tc.tq = nq <= 4 ? 4 : (nq <= 8 ? 8 : 16);
             tc.n_qtiles = 1;
             tc.smem = (size_t)tc.tq * dpad;
+            pl->fused = stream_cfg(di, nq, d);
         } else {
             tc.stream = false;
             tc.nw = nq >= 1024 ? 16 : 8;
@@ -1061,7 +1134,7 @@ bool make_plan(const DevInfo &di, long long nq, long long n, int d, int k, bool 
     const size_t list = (size_t)nq * (size_t)k * 8;
     pl->off_parts_full = take((size_t)pl->full.splits * list);
     size_t tmp_parts = pl->full.splits > kMergePPW ? (size_t)((pl->full.splits + kMergePPW - 1) / kMergePPW) : 0;
-    pl->off_parts_samp = pl->off_thr = pl->off_thrd = pl->off_cnt = pl->off_flags = pl->off_cand = pl->off_mins = 0;
+    pl->off_parts_samp = pl->off_thr = pl->off_thrd = pl->off_ctl = pl->off_cnt = pl->off_flags = pl->off_cand = pl->off_mins = 0;
     if (pl->thresh) {
         if (!pl->bounded) {
             pl->off_parts_samp = take((size_t)pl->samp.splits * list);
@@ -1071,7 +1144,8 @@ bool make_plan(const DevInfo &di, long long nq, long long n, int d, int k, bool 
             pl->off_thrd = take((size_t)nq * sizeof(unsigned int));
             pl->off_mins = pl->tc.stream ? take((size_t)16 * kMinSlots * sizeof(unsigned int)) : 0;
         }
-        pl->off_cnt = take((size_t)nq * sizeof(int));
+        pl->off_ctl = take(256);          // grid-barrier counter + in-kernel bounds of the fused streaming kernel;
+        pl->off_cnt = take((size_t)nq * sizeof(int));   // directly followed by the candidate counters (one memset)
         pl->off_flags = take((size_t)nq * sizeof(int));
         pl->off_cand = take((size_t)nq * (size_t)pl->cmax * 8);
     }
@@ -1144,6 +1218,37 @@ int run_merge(const unsigned long long *keys, long long parts, long long nq, int
     return DCTD_OK;
 }
 
+// instantiations of the fused streaming kernel.  d = 480 (the reference's fingerprints, 30 chunks): chunk count known
+// at compile time; otherwise runtime
+template <int NW, int TD, int VAR = 0>
+const void *stream_kernel_n(int tq, bool c480) {
+#define DCTD_SK(TQ_) (c480 ? (const void *)l1_stream_fused_kernel<TQ_, NW, TD, 30, VAR> : (const void *)l1_stream_fused_kernel<TQ_, NW, TD, 0, VAR>)
+    switch (tq) {
+        case 4: return DCTD_SK(4);
+        case 8: return DCTD_SK(8);
+        case 12: return DCTD_SK(12);
+        case 16: return DCTD_SK(16);
+    }
+#undef DCTD_SK
+    return nullptr;
+}
+
+const void *stream_kernel(const StreamCfg &c, int d) {
+    const bool c480 = d == 480;
+    switch (c.nw * 10 + c.td) {
+        case 71: return stream_kernel_n<7, 1>(c.tq, c480);
+        case 41: return stream_kernel_n<4, 1>(c.tq, c480);
+        case 21: return stream_kernel_n<2, 1>(c.tq, c480);
+        case 11: return stream_kernel_n<1, 1>(c.tq, c480);
+#ifdef DCTD_TUNING
+        case 42: return g_l1_var == 1 ? stream_kernel_n<4, 2, 1>(c.tq, c480) : (g_l1_var == 2 ? stream_kernel_n<4, 2, 2>(c.tq, c480) : stream_kernel_n<4, 2>(c.tq, c480));
+        case 62: return stream_kernel_n<6, 2>(c.tq, c480);
+        case 52: return g_l1_var == 1 ? stream_kernel_n<5, 2, 1>(c.tq, c480) : (g_l1_var == 2 ? stream_kernel_n<5, 2, 2>(c.tq, c480) : stream_kernel_n<5, 2>(c.tq, c480));
+#endif
+    }
+    return nullptr;
+}
+
 // The search proper.  Result as (dist, ids) and / or packed keys.  `bound` (optional, device int32 [nq]): only vectors
 // with distance <= bound[q] need to be reported for query q (the caller knows that the k best over ALL shards lie within).
 int run_topk(const int8_t *d_q, int64_t nq, const void *d_packed, int64_t n, int32_t d, int32_t k, int64_t id_base,
@@ -1181,85 +1286,109 @@ int run_topk(const int8_t *d_q, int64_t nq, const void *d_packed, int64_t n, int
     int *cnt = (int *)(ws + pl.off_cnt);
     int *flagsq = (int *)(ws + pl.off_flags);
     unsigned long long *cand = (unsigned long long *)(ws + pl.off_cand);
-    const unsigned int *thrd = nullptr;
-    bool skip_sample = false;
-    if (pl.bounded) {
-        // 1'. the caller's bounds; nothing is seeded, every group is scanned
-        thrd = (const unsigned int *)d_bound;
-        DCTD_CUDA_TRY(cudaMemsetAsync(cnt, 0, (size_t)nq * sizeof(int), stream));
-    } else {
-        unsigned long long *parts_samp = (unsigned long long *)(ws + pl.off_parts_samp);
-        unsigned long long *thr = (unsigned long long *)(ws + pl.off_thr);
-        unsigned int *thrw = (unsigned int *)(ws + pl.off_thrd);
-        thrd = thrw;
-        // 1. thresholds: from lane minima over every gstride-th group (few queries), or the exact top-k of that sample
-        if (pl.tc.stream && g_l1_mode != 2) {
-            ScanParams s1 = sp;
-            s1.gstride = pl.gstride;
-            s1.n_groups = pl.samp_groups;
-            unsigned int *mins = (unsigned int *)(ws + pl.off_mins);
-            typedef void (*MinFn)(const ScanParams, unsigned int *, int);
-            const int tq = pl.tc.tq;
-            MinFn fn = tq == 4 ? l1_sample_min_kernel<4> : (tq == 8 ? l1_sample_min_kernel<8> : l1_sample_min_kernel<16>);
-            // every slot below samp_m is written (lanes that saw no vector write 0xffffffff = "no bound")
-            fn<<<pl.samp_grid, 128, pl.tc.smem, stream>>>(s1, mins, pl.samp_red);
-            DCTD_LAUNCH_CHECK();
-            l1_kth_kernel<<<(unsigned)nq, 256, 0, stream>>>(mins, pl.samp_m, k, thrw, cnt);   // also zeroes cnt
-            DCTD_LAUNCH_CHECK();
-        } else {
-            ScanParams s1 = sp;
-            s1.parts = parts_samp;
-            s1.gstride = pl.gstride;
-            int rc = launch_heap(pl.samp, s1, stream);
-            if (rc != DCTD_OK) return rc;
-            rc = run_merge(parts_samp, pl.samp.splits, nq, k, 0, nullptr, nullptr, thr, nullptr, tmp, stream);
-            if (rc != DCTD_OK) return rc;
-            // the sample's top-k seeds the candidate lists (then the scan can leave the sampled groups out)
-            skip_sample = !pl.tc.stream && g_l1_mode != 3;
-            l1_seed_kernel<<<(unsigned)((nq + 3) / 4), 128, 0, stream>>>(thr, nq, k, cand, cnt, pl.cmax, skip_sample, thrw);
-            DCTD_LAUNCH_CHECK();
-        }
-    }
-    // 2. one pass over the database: append everything within the bound
-    {
-        ScanParams s2 = sp;
-        s2.thr_dist = thrd; s2.cand = cand; s2.cnt = cnt; s2.cmax = pl.cmax;
-        s2.n_groups = (n + 31) / 32;
-        const ThreshConfig &tc = pl.tc;
-        if (skip_sample) {       // every group but the sampled ones
-            s2.skip = pl.gstride;
-            s2.n_groups -= (s2.n_groups + pl.gstride - 1) / pl.gstride;
-        }
-        if (tc.stream) {
-            ScanFn fn = tc.tq == 4 ? l1_thresh_stream_kernel<4> : (tc.tq == 8 ? l1_thresh_stream_kernel<8> : l1_thresh_stream_kernel<16>);
-            int per_sm = 0;
-            DCTD_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, 128, tc.smem));
-            const long long want = std::max<long long>(1, (s2.n_groups + 3) / 4);
-            const int grid = (int)std::min<long long>(want, di.sms * std::max(1, per_sm));
-            fn<<<grid, 128, tc.smem, stream>>>(s2);
-            DCTD_LAUNCH_CHECK();
-        } else {
-            s2.groups_per_split = tc.groups_per_split;
-            ScanFn fn;
-            if (tc.nw == 16 && d == 480 && g_l1_mode != 5) fn = l1_thresh_scan_kernel<16, 8, kTDmax, kStagesMax, 30>;
-            else if (tc.nw == 16) fn = l1_thresh_scan_kernel<16, 8, kTDmax, kStagesMax>;
-            else if (tc.tq == 8) fn = l1_thresh_scan_kernel<8, 8, kTDmax, kStagesMax>;
-            else fn = l1_thresh_scan_kernel<8, 4, kTDmax, kStagesMax>;
-            if (tc.n_qtiles > 65535) return DCTD_ERR_UNSUPPORTED;
-            DCTD_CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc.smem));
-            fn<<<dim3((unsigned)tc.splits, (unsigned)tc.n_qtiles), (tc.nw + 1) * 32, tc.smem, stream>>>(s2);
-            DCTD_LAUNCH_CHECK();
-        }
-    }
-    // 3. exact selection per query; overflowed queries are flagged
-    {
-        SelectParams se{};
-        se.cand = cand; se.cnt = cnt; se.cmax = pl.cmax; se.k = k; se.nq = nq; se.id_base = id_base;
-        se.dist = d_dist; se.ids = ids; se.key_out = keys_out; se.qflags = flagsq;
-        const size_t ssmem = (size_t)pl.cmax * 8;
-        DCTD_CUDA_TRY(cudaFuncSetAttribute(l1_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssmem));
-        l1_select_kernel<<<(unsigned)nq, 256, ssmem, stream>>>(se);
+    SelectParams se{};
+    se.cand = cand; se.cnt = cnt; se.cmax = pl.cmax; se.k = k; se.nq = nq; se.id_base = id_base;
+    se.dist = d_dist; se.ids = ids; se.key_out = keys_out; se.qflags = flagsq;
+    const void *fused_fn = (pl.tc.stream && pl.fused.ok && g_l1_mode != 2 && g_l1_mode != 9) ? stream_kernel(pl.fused, d) : nullptr;
+    if (fused_fn) {
+        // ---- few queries: sample, bound, stream and selection in ONE cooperative launch (l1_stream.cuh) ----
+        char *ctl = ws + pl.off_ctl;
+        DCTD_CUDA_TRY(cudaMemsetAsync(ctl, 0, (pl.off_cnt - pl.off_ctl) + (size_t)nq * sizeof(int), stream));
+        StreamParams P{};
+        P.sp = sp;
+        P.sp.gstride = pl.gstride;
+        P.sp.thr_dist = pl.bounded ? (const unsigned int *)d_bound : nullptr;
+        P.sp.cand = cand; P.sp.cnt = cnt; P.sp.cmax = pl.cmax;
+        P.se = se;
+        P.mins = pl.bounded ? nullptr : (unsigned int *)(ws + pl.off_mins);
+        P.bar = (unsigned int *)ctl;
+        P.thr_out = (unsigned int *)(ctl + 64);
+        P.stages = pl.fused.stages;
+        P.m = (int)std::min<long long>(di.sms * pl.fused.nw, kMinSlots);
+        P.kscr_n = pl.fused.kscr_n;
+        DCTD_CUDA_TRY(cudaFuncSetAttribute(fused_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.fused.smem));
+        void *args[] = {&P};
+        DCTD_CUDA_TRY(cudaLaunchCooperativeKernel(fused_fn, dim3((unsigned)di.sms), dim3((pl.fused.nw + 1) * 32), args,
+                                                  pl.fused.smem, stream));
         DCTD_LAUNCH_CHECK();
+    } else {
+        const unsigned int *thrd = nullptr;
+        bool skip_sample = false;
+        if (pl.bounded) {
+            // 1'. the caller's bounds; nothing is seeded, every group is scanned
+            thrd = (const unsigned int *)d_bound;
+            DCTD_CUDA_TRY(cudaMemsetAsync(cnt, 0, (size_t)nq * sizeof(int), stream));
+        } else {
+            unsigned long long *parts_samp = (unsigned long long *)(ws + pl.off_parts_samp);
+            unsigned long long *thr = (unsigned long long *)(ws + pl.off_thr);
+            unsigned int *thrw = (unsigned int *)(ws + pl.off_thrd);
+            thrd = thrw;
+            // 1. thresholds: from lane minima over every gstride-th group (few queries), or the exact top-k of that sample
+            if (pl.tc.stream && g_l1_mode != 2) {
+                ScanParams s1 = sp;
+                s1.gstride = pl.gstride;
+                s1.n_groups = pl.samp_groups;
+                unsigned int *mins = (unsigned int *)(ws + pl.off_mins);
+                typedef void (*MinFn)(const ScanParams, unsigned int *, int);
+                const int tq = pl.tc.tq;
+                MinFn fn = tq == 4 ? l1_sample_min_kernel<4> : (tq == 8 ? l1_sample_min_kernel<8> : l1_sample_min_kernel<16>);
+                // every slot below samp_m is written (lanes that saw no vector write 0xffffffff = "no bound")
+                fn<<<pl.samp_grid, 128, pl.tc.smem, stream>>>(s1, mins, pl.samp_red);
+                DCTD_LAUNCH_CHECK();
+                l1_kth_kernel<<<(unsigned)nq, 256, 0, stream>>>(mins, pl.samp_m, k, thrw, cnt);   // also zeroes cnt
+                DCTD_LAUNCH_CHECK();
+            } else {
+                ScanParams s1 = sp;
+                s1.parts = parts_samp;
+                s1.gstride = pl.gstride;
+                int rc = launch_heap(pl.samp, s1, stream);
+                if (rc != DCTD_OK) return rc;
+                rc = run_merge(parts_samp, pl.samp.splits, nq, k, 0, nullptr, nullptr, thr, nullptr, tmp, stream);
+                if (rc != DCTD_OK) return rc;
+                // the sample's top-k seeds the candidate lists (then the scan can leave the sampled groups out)
+                skip_sample = !pl.tc.stream && g_l1_mode != 3;
+                l1_seed_kernel<<<(unsigned)((nq + 3) / 4), 128, 0, stream>>>(thr, nq, k, cand, cnt, pl.cmax, skip_sample, thrw);
+                DCTD_LAUNCH_CHECK();
+            }
+        }
+        // 2. one pass over the database: append everything within the bound
+        {
+            ScanParams s2 = sp;
+            s2.thr_dist = thrd; s2.cand = cand; s2.cnt = cnt; s2.cmax = pl.cmax;
+            s2.n_groups = (n + 31) / 32;
+            const ThreshConfig &tc = pl.tc;
+            if (skip_sample) {       // every group but the sampled ones
+                s2.skip = pl.gstride;
+                s2.n_groups -= (s2.n_groups + pl.gstride - 1) / pl.gstride;
+            }
+            if (tc.stream) {
+                ScanFn fn = tc.tq == 4 ? l1_thresh_stream_kernel<4> : (tc.tq == 8 ? l1_thresh_stream_kernel<8> : l1_thresh_stream_kernel<16>);
+                int per_sm = 0;
+                DCTD_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, 128, tc.smem));
+                const long long want = std::max<long long>(1, (s2.n_groups + 3) / 4);
+                const int grid = (int)std::min<long long>(want, di.sms * std::max(1, per_sm));
+                fn<<<grid, 128, tc.smem, stream>>>(s2);
+                DCTD_LAUNCH_CHECK();
+            } else {
+                s2.groups_per_split = tc.groups_per_split;
+                ScanFn fn;
+                if (tc.nw == 16 && d == 480 && g_l1_mode != 5) fn = l1_thresh_scan_kernel<16, 8, kTDmax, kStagesMax, 30>;
+                else if (tc.nw == 16) fn = l1_thresh_scan_kernel<16, 8, kTDmax, kStagesMax>;
+                else if (tc.tq == 8) fn = l1_thresh_scan_kernel<8, 8, kTDmax, kStagesMax>;
+                else fn = l1_thresh_scan_kernel<8, 4, kTDmax, kStagesMax>;
+                if (tc.n_qtiles > 65535) return DCTD_ERR_UNSUPPORTED;
+                DCTD_CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc.smem));
+                fn<<<dim3((unsigned)tc.splits, (unsigned)tc.n_qtiles), (tc.nw + 1) * 32, tc.smem, stream>>>(s2);
+                DCTD_LAUNCH_CHECK();
+            }
+        }
+        // 3. exact selection per query; overflowed queries are flagged
+        {
+            const size_t ssmem = (size_t)pl.cmax * 8;
+            DCTD_CUDA_TRY(cudaFuncSetAttribute(l1_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssmem));
+            l1_select_kernel<<<(unsigned)nq, 256, ssmem, stream>>>(se);
+            DCTD_LAUNCH_CHECK();
+        }
     }
     // 4. flagged queries (candidate list overflow: heavy distance ties, adversarial order, a bound that is not one)
     //    are redone by the heap scan; CTAs of unflagged query tiles exit at once, so this costs a few microseconds
@@ -1302,6 +1431,16 @@ extern "C" {
 
 #ifdef DCTD_TUNING
 int dctd_l1_set_mode(int mode) { g_l1_mode = mode; return DCTD_OK; }
+
+// phase stamps (ns, globaltimer) of CTA 0 of the last fused streaming launch that used this workspace: 8 values
+int dctd_l1_stream_stamps(const void *d_workspace, int64_t nq, int64_t n, int32_t d, int32_t k, uint64_t *h_out8) {
+    DevInfo di;
+    dev_info(&di);
+    TopkPlan pl;
+    if (!make_plan(di, nq, n, d, k, false, &pl) || !pl.thresh) return DCTD_ERR_ARG;
+    DCTD_CUDA_TRY(cudaMemcpy(h_out8, (const char *)d_workspace + pl.off_ctl + 128, 64, cudaMemcpyDeviceToHost));
+    return DCTD_OK;
+}
 #endif
 
 size_t dctd_l1_packed_bytes(int64_t n, int32_t d) {
