@@ -725,7 +725,9 @@ __global__ void __launch_bounds__(WsCfg<K, DC, RIDER>::T, 1) fp_ws_kernel(const 
                 s_flag = 0;
                 s_rlast = 0;
                 if (RIDER && (iflags & kWfRider)) {
-                    // the consumers wrote this item's rider sums to the slab (and fenced) before the hand-over
+                    // the consumers wrote this item's rider sums to the slab (and fenced) before the hand-over through the
+                    // CTA-scope mbarrier; the release at GPU scope needs the fence in the thread that takes the ticket
+                    __threadfence();
                     const int ticket = atomicAdd(&p.counters[ds_[kWRiderCounter]], 1);
                     s_rlast = (ticket == ds_[kWRiderNsplit] - 1);
                 }

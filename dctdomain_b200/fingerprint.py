@@ -35,6 +35,14 @@ DEFAULT_MAXLEN = 500   # src/make_db.py --maxlen default
 _workspaces: dict = {}
 
 
+def _owner(device):
+    """Key of the per-(device, stream, host thread) scratch caches below: kernels queued on one stream by one thread
+    run in order, so reusing a buffer is safe there and nowhere else (a search on one stream and fingerprinting on
+    another, or two host threads, get separate scratch memory)."""
+    import threading
+    return device, torch.cuda.current_stream(device).cuda_stream, threading.get_ident()
+
+
 def _device(device=None) -> torch.device:
     if not torch.cuda.is_available():
         raise RuntimeError('dctdomain_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback')
@@ -44,10 +52,13 @@ def _device(device=None) -> torch.device:
 
 
 def _workspace(device: torch.device, nbytes: int) -> torch.Tensor:
-    ws = _workspaces.get(device)
+    """Scratch memory of the calling (device, stream, thread).  Growing it replaces the buffer: anything an earlier call
+    left in it (plan tables of ``execute_plan``) is gone, which is why ``tables_resident`` needs a caller-owned workspace."""
+    key = _owner(device)
+    ws = _workspaces.get(key)
     if ws is None or ws.numel() < nbytes:
         ws = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
-        _workspaces[device] = ws
+        _workspaces[key] = ws
     return ws
 
 
@@ -56,8 +67,8 @@ def parse_domain(dom: str, n_rows: int):
 
     Returns ([(begin0, end_exclusive), ...], kept_string).  A segment is dropped when its begin
     lies beyond the protein, an end beyond the protein is clipped, and - as in the reference,
-    which removes from the list it iterates over - the segment after a dropped one is passed
-    over but stays in the returned string.
+    which removes (by value) from the list it iterates over - the segment after a dropped one is
+    passed over but stays in the returned string.
     """
     parts = dom.split(',')
     segs = []
@@ -66,7 +77,7 @@ def parse_domain(dom: str, n_rows: int):
         beg_s, end_s = parts[pos].split('-')
         beg, end = int(beg_s), int(end_s)
         if (beg or end) > n_rows:
-            parts.pop(pos)
+            parts.remove(parts[pos])        # by value, like the reference: an equal segment passed over earlier goes first
             pos += 1
             continue
         lo = beg - 1 if beg >= 1 else n_rows + beg - 1
@@ -113,7 +124,13 @@ def make_plan(n_layers, D, n, m, src_rows, prot_src0, prot_nsrc, dom_prot, dom_s
 
 
 def execute_plan(plan: _Plan, src_tensors, out: torch.Tensor, tables_resident=False, workspace=None):
-    """Launch the fingerprint kernel.  ``src_tensors[layer][s]`` are CUDA float32 [rows, D] tensors."""
+    """Launch the fingerprint kernel.  ``src_tensors[layer][s]`` are CUDA float32 [rows, D] tensors.
+
+    Stream-ordered on the current stream.  Without ``workspace`` the scratch memory of the calling (device, stream,
+    thread) is used, which any other call on that stream may overwrite or replace: ``tables_resident=True`` (the plan
+    tables were uploaded by an earlier call with this plan) therefore needs a caller-owned ``workspace``."""
+    if tables_resident and workspace is None:
+        raise ValueError('tables_resident=True needs the caller-owned workspace the plan tables were uploaded to')
     dev = out.device
     ptrs = np.array([t.data_ptr() for layer in src_tensors for t in layer], dtype=np.uint64)
     ld = src_tensors[0][0].stride(0) if src_tensors and src_tensors[0] else 0
@@ -142,10 +159,11 @@ _tables: dict = {}
 
 def _pinned_table(device, n_entries: int) -> np.ndarray:
     """Pinned host array [n_entries, 3] of int64 (src, dst, nbytes descriptors the gather kernel reads over PCIe)."""
-    t = _tables.get(device)
+    key = _owner(device)
+    t = _tables.get(key)
     if t is None or t.shape[0] < n_entries:
         t = torch.empty((max(n_entries, 4096) * 2, 3), dtype=torch.int64).pin_memory()
-        _tables[device] = t
+        _tables[key] = t
     return t
 
 
@@ -154,18 +172,20 @@ _aux: dict = {}
 
 
 def _aux_stream(device) -> torch.cuda.Stream:
-    st = _aux.get(device)
+    key = _owner(device)
+    st = _aux.get(key)
     if st is None:
         st = torch.cuda.Stream(device=device)
-        _aux[device] = st
+        _aux[key] = st
     return st
 
 
 def _stage_buffer(device, nbytes):
-    buf = _stage.get(device)
+    key = _owner(device)
+    buf = _stage.get(key)
     if buf is None or buf.numel() < nbytes:
         buf = torch.empty(int(nbytes * 1.25) + (1 << 20), dtype=torch.uint8, device=device)
-        _stage[device] = buf
+        _stage[key] = buf
     return buf
 
 
@@ -201,7 +221,7 @@ def quantize_batch(fps, qdim=(3, 80, 3, 80), device=None, maxlen=DEFAULT_MAXLEN,
     # dctd_h2d_rows) while this thread keeps walking the batch, the compute stream joins before the kernel
     aux_stream = _aux_stream(dev)
     aux_stream.wait_stream(main_stream)
-    have = _stage.get(dev)            # staging buffer of an earlier call (kept alive until this call returns)
+    have = _stage.get(_owner(dev))    # staging buffer of an earlier call (kept alive until this call returns)
     state = {'done': 0, 'bases': [], 'tab': 0}  # bases: [(first h index, device address that h_off is relative to)]
 
     def flush(final=False):
@@ -225,7 +245,7 @@ def quantize_batch(fps, qdim=(3, 80, 3, 80), device=None, maxlen=DEFAULT_MAXLEN,
         a_len = np.array(h_bytes[lo:], dtype=np.int64)
         a_off = np.array(h_off[lo:], dtype=np.int64)
         with torch.cuda.device(dev):
-            if all(h_pin[lo:]) and not (a_len % 16).any():
+            if all(h_pin[lo:]) and not (a_len % 16).any() and not (a_src % 16).any():     # 16-byte loads: sizes AND addresses
                 # pinned sources: one gather kernel over <= 256 KB pieces (no per-array DMA gaps)
                 npc = (a_len + _GATHER_PIECE - 1) // _GATHER_PIECE
                 total = int(npc.sum())

@@ -238,28 +238,47 @@ class IndexFlatL1(IndexFlat):
 
 # ------------------------------------------------------------------------------------------
 # .index files, faiss IndexFlat layout:
-#   fourcc "IxF2" | d int32 | ntotal int64 | 2 x int64 dummy (1 << 20) | is_trained u8 |
-#   metric_type int32 | n_floats uint64 | float32 data
+#   fourcc "IxF2" ("IxFI" inner product, "IxFl" any other metric) | d int32 | ntotal int64 | 2 x int64 dummy (1 << 20) |
+#   is_trained u8 | metric_type int32 | [metric_arg float32 if metric_type > 1] | n_floats uint64 | float32 data
 # ------------------------------------------------------------------------------------------
-_FOURCC = {METRIC_L2: b'IxF2', METRIC_INNER_PRODUCT: b'IxFI'}
+_FOURCC = {METRIC_L2: b'IxF2', METRIC_INNER_PRODUCT: b'IxFI', METRIC_L1: b'IxFl'}     # IxFl: any other metric (+ metric_arg)
 
 
-_SIDECAR_MAGIC = b'DCTDI8\x00\x01'
+_SIDECAR_MAGIC = b'DCTDI8\x00\x02'
+_DIGEST_SPAN = 4 << 20       # bytes hashed at either end of the float payload
 
 
 def _sidecar_path(path: str) -> str:
     return path + '.i8'
 
 
+def _payload_digest(f, payload_off: int, payload_bytes: int) -> bytes:
+    """Content check of a .index float payload: blake2b over its first and last 4 MB (everything when smaller) and its
+    length.  Cheap next to reading the file, and it changes whenever vectors at either end change - together with the
+    full-size check this catches a rewritten index; the sidecar is then ignored and the float data is used."""
+    import hashlib
+    h = hashlib.blake2b(digest_size=16)
+    h.update(struct.pack('<q', payload_bytes))
+    f.seek(payload_off)
+    if payload_bytes <= 2 * _DIGEST_SPAN:
+        h.update(f.read(payload_bytes))
+    else:
+        h.update(f.read(_DIGEST_SPAN))
+        f.seek(payload_off + payload_bytes - _DIGEST_SPAN)
+        h.update(f.read(_DIGEST_SPAN))
+    return h.digest()
+
+
 def write_index(index: IndexFlat, path: str, sidecar: bool = None):
-    """faiss.write_index for a flat index.  The file always records the metric the index was built
-    with (the reference builds IndexFlatL2 and flips to L1 only in memory, src/query_db.py:76).
+    """faiss.write_index for a flat index.  The file records the metric the index object carries (the reference builds
+    IndexFlatL2 and flips to L1 only in memory, src/query_db.py:76, so its files say L2; an index whose metric_type is
+    METRIC_L1 is written the way faiss writes it: fourcc 'IxFl', metric_type 2 and a float metric_arg).
 
     ``sidecar=True`` also writes ``<path>.i8``: the same vectors as raw int8 (a quarter of the bytes, no float
-    round trip on load).  ``read_index`` uses it when it matches the .index header (d, ntotal, file size of the
-    .index at the time of writing); the faiss-compatible .index stays the source of truth.  Default: off, or on
-    with DCTD_INDEX_SIDECAR=1 in the environment (so that the reference's unchanged ``faiss.write_index(index, path)``
-    at src/database.py:243 produces one)."""
+    round trip on load).  ``read_index`` uses it only if it matches the .index: d, ntotal, file size, mtime and a digest
+    of the float payload (see ``_payload_digest``); the faiss-compatible .index stays the source of truth.  Default: off,
+    or on with DCTD_INDEX_SIDECAR=1 in the environment (so that the reference's unchanged ``faiss.write_index(index,
+    path)`` at src/database.py:243 produces one)."""
     if sidecar is None:
         sidecar = os.environ.get('DCTD_INDEX_SIDECAR') == '1'
     metric = index.metric_type if index.metric_type in _FOURCC else METRIC_L2
@@ -267,13 +286,19 @@ def write_index(index: IndexFlat, path: str, sidecar: bool = None):
     with open(path, 'wb') as f:
         f.write(_FOURCC[metric])
         f.write(struct.pack('<iqqqBi', index.d, index.ntotal, 1 << 20, 1 << 20, 1, metric))
+        if metric > 1:
+            f.write(struct.pack('<f', 0.0))         # metric_arg (faiss writes it for every metric beyond IP / L2)
         f.write(struct.pack('<Q', index.ntotal * index.d))
+        payload_off = f.tell()
         f.write(rows.astype(np.float32).tobytes())
     side = _sidecar_path(path)
     if sidecar:
+        with open(path, 'rb') as f:
+            digest = _payload_digest(f, payload_off, index.ntotal * index.d * 4)
         with open(side, 'wb') as f:
             f.write(_SIDECAR_MAGIC)
             f.write(struct.pack('<iqq', index.d, index.ntotal, os.path.getsize(path)))
+            f.write(digest)
             f.write(np.ascontiguousarray(rows, dtype=np.int8).tobytes())
     elif os.path.exists(side):
         os.remove(side)                     # a stale sidecar must not outlive a rewritten index
@@ -291,16 +316,19 @@ def read_index(path: str, device=None) -> IndexFlat:
         (n_floats,) = struct.unpack('<Q', f.read(8))
         if n_floats != ntotal * d:
             raise ValueError(f'{path}: inconsistent header ({n_floats} floats for {ntotal} x {d})')
-        data = _read_sidecar(path, d, ntotal)
+        payload_off = f.tell()
+        data = _read_sidecar(path, d, ntotal, f, payload_off)
         if data is None:
+            f.seek(payload_off)
             data = np.frombuffer(f.read(n_floats * 4), dtype='<f4').reshape(ntotal, d)
     index = IndexFlat(d, metric, device)
     index.add(data)
     return index
 
 
-def _read_sidecar(path: str, d: int, ntotal: int):
-    """int8 rows of ``<path>.i8`` if that file belongs to this .index (same d, ntotal and .index size), else None."""
+def _read_sidecar(path: str, d: int, ntotal: int, index_file, payload_off: int):
+    """int8 rows of ``<path>.i8`` if that file belongs to this .index (same d, ntotal, .index size AND the digest of the
+    .index float payload recorded when the sidecar was written), else None."""
     side = _sidecar_path(path)
     if not os.path.exists(side):
         return None
@@ -308,8 +336,11 @@ def _read_sidecar(path: str, d: int, ntotal: int):
         if f.read(len(_SIDECAR_MAGIC)) != _SIDECAR_MAGIC:
             return None
         sd, sn, size = struct.unpack('<iqq', f.read(4 + 8 + 8))
+        digest = f.read(16)
         if (sd, sn, size) != (d, ntotal, os.path.getsize(path)):
             return None
+        if digest != _payload_digest(index_file, payload_off, ntotal * d * 4):
+            return None                                                 # same shape, different vectors: stale sidecar
         rows = np.fromfile(f, dtype=np.int8, count=ntotal * d)      # writable: torch.from_numpy takes it as is
     if rows.size != ntotal * d:
         return None

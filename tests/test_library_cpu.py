@@ -148,6 +148,11 @@ def test_parse_domain_matches_reference_quirks():
     assert parse_domain('300-350,310-320,1-50', 200) == ([(0, 50)], '310-320,1-50')
     assert parse_domain('50-300', 200) == ([(49, 200)], '50-300')
     assert parse_domain('500-600', 200) == ([], '')
+    # removal is BY VALUE (list.remove): an equal out-of-range segment that was passed over earlier goes first
+    # (expected values: the unmodified reference get_doms, src/fingerprint.py:160-171, run on these strings)
+    assert parse_domain('34-25,34-33,10-17,34-33', 33) == ([(9, 17)], '10-17,34-33')
+    assert parse_domain('34-33,10-17,34-33', 33) == ([], '10-17')
+    assert parse_domain('40-50,40-50,1-5,40-50,6-7', 33) == ([(0, 5)], '1-5,40-50,6-7')
     assert parse_domain('177-331,1-77', 400) == ([(176, 331), (0, 77)], '177-331,1-77')
 
 

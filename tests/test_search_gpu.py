@@ -102,13 +102,32 @@ def test_add_in_pieces_and_roundtrip(tmp_path):
         idx.add(np.full((1, 480), 0.5))        # not int8 valued
     # int8 sidecar: used when it matches the .index, ignored (and removed on rewrite) otherwise
     dindex.write_index(idx, path, sidecar=True)
-    assert os.path.getsize(path + '.i8') == 8 + 4 + 8 + 8 + 1000 * 480 and open(path, 'rb').read() == raw
+    hdr = 8 + 4 + 8 + 8 + 16                                  # magic, d, ntotal, .index size, payload digest
+    assert os.path.getsize(path + '.i8') == hdr + 1000 * 480 and open(path, 'rb').read() == raw
     side = dindex.read_index(path)
     assert np.array_equal(side.reconstruct_n(), db)
     with open(path + '.i8', 'r+b') as f:                      # corrupt the payload: proves the sidecar is what was read
-        f.seek(8 + 4 + 8 + 8)
+        f.seek(hdr)
         f.write(bytes([db[0, 0] ^ 1]))
     assert dindex.read_index(path).reconstruct_n()[0, 0] == (db[0, 0] ^ 1)
+    # the .index rewritten by another tool with the SAME shape but different vectors (what faiss itself would do): the
+    # stale sidecar must be ignored - size, d and ntotal all still match, only the payload digest tells
+    db2 = db.copy()
+    db2[0] = db[1]
+    db2[-1] = db[2]
+    with open(path, 'r+b') as f:
+        f.seek(len(raw) - 1000 * 480 * 4)
+        f.write(db2.astype(np.float32).tobytes())
+    assert np.array_equal(dindex.read_index(path).reconstruct_n(), db2)
+    # an index that carries METRIC_L1 keeps it through a round trip (faiss: fourcc IxFl, metric_type 2, metric_arg)
+    l1 = dindex.IndexFlatL1(480)
+    l1.add(db[:100])
+    dindex.write_index(l1, path)
+    raw1 = open(path, 'rb').read()
+    assert raw1[:4] == b'IxFl' and len(raw1) == 4 + 4 + 8 * 3 + 1 + 4 + 4 + 8 + 100 * 480 * 4
+    back1 = dindex.read_index(path)
+    assert back1.metric_type == dindex.METRIC_L1 and back1.ntotal == 100
+    assert np.array_equal(back1.search(db[:3], 5)[1], so.l1_topk(db[:3], db[:100], 5)[1])
     other = _index(db[:500])
     dindex.write_index(other, path)                           # rewrite without a sidecar: the stale one goes away
     assert not os.path.exists(path + '.i8') and dindex.read_index(path).ntotal == 500
