@@ -48,21 +48,41 @@ def batch_lengths(seed: int, n: int) -> np.ndarray:
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU reference arm (oracle port of src/fingerprint.py under multiprocessing.Pool, like make_db --cpu N)
+# CPU reference arm: the reference's own Fingerprint.quantize under multiprocessing.Pool, like make_db --cpu N
 # ------------------------------------------------------------------------------------------------
 _CPU_EMB = None
+REF_DIR = os.path.join(ROOT, 'baseline', '_ref')      # verbatim copy of the reference's src/*.py (scripts/install_reference.py)
+
+
+def reference_fingerprint_class():
+    """(Fingerprint class, kind): the UNMODIFIED reference class from baseline/_ref (kind 'reference'), or None when it
+    is not installed (then the oracle port stands in, kind 'port')."""
+    if os.path.exists(os.path.join(REF_DIR, 'fingerprint.py')):
+        import importlib.util
+        spec = importlib.util.spec_from_file_location('dctd_reference_fingerprint', os.path.join(REF_DIR, 'fingerprint.py'))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        return mod.Fingerprint, 'reference'
+    return None, 'port'
+
+
+_REF_CLS = None
 
 
 def _cpu_task(i):
-    from oracle import fingerprint_oracle as fo
     emb = _CPU_EMB[i % len(_CPU_EMB)]
     L = emb[15].shape[0]
+    if _REF_CLS is not None:          # reference src/make_db.py:29: fp.quantize([3, 80, 3, 80]) in a Pool worker
+        fp = _REF_CLS(pid=f'p{i}', seq='', embed=emb, domains=[f'1-{L}'], quants={})
+        fp.quantize(QDIM)
+        return int(fp.quants[f'1-{L}'].sum())
+    from oracle import fingerprint_oracle as fo
     q, _ = fo.quantize_faithful(emb, [f'1-{L}'], QDIM)
     return int(q[f'1-{L}'].sum())
 
 
 class CpuArm:
-    """The reference's CPU path: the faithful oracle port of fingerprint.py quantize under
+    """The reference's CPU path: ``Fingerprint.quantize`` of the unmodified reference module (baseline/_ref) under
     multiprocessing.Pool(cores), the `make_db.py --cpu N` pattern (src/make_db.py:48-49).  The pool and the input
     embeddings are created once (workers are forked after the inputs exist: no pickling of embeddings, which the
     reference does pay); `rate(n)` times one pool.map over n domains."""
@@ -70,12 +90,17 @@ class CpuArm:
     def __init__(self, cores: int, distinct: int = 64):
         import multiprocessing as mp
         import synth
-        global _CPU_EMB
+        global _CPU_EMB, _REF_CLS
+        _REF_CLS, self.kind = reference_fingerprint_class()
         lens = batch_lengths(12345, distinct)
         _CPU_EMB = [synth.layers(900 + i, int(L), D, 'white') for i, L in enumerate(lens)]
         self.cores = cores
         self.pool = mp.get_context('fork').Pool(cores)
         self.pool.map(_cpu_task, range(cores))                  # warm the workers
+
+    def what(self):
+        return ('unmodified reference src/fingerprint.py Fingerprint.quantize (baseline/_ref)' if self.kind == 'reference'
+                else 'oracle port of reference fingerprint.py quantize (baseline/_ref not installed)')
 
     def rate(self, n_domains: int):
         t0 = time.perf_counter()
@@ -86,6 +111,13 @@ class CpuArm:
     def close(self):
         self.pool.close()
         self.pool.join()
+
+
+def primary_config(batch, pool, world):
+    """`config` of the primary line - the same dict for our arm and for the reference arm (same workload)."""
+    return {'workload': workload_name(batch), 'domains_per_step': batch, 'resident_batches': pool,
+            'l2': 'inputs larger than L2 (a step streams the embeddings of domains_per_step domains, ~2.8 MB each on average)',
+            'parallelism': f'domains sharded over {world} rank(s), no collective'}
 
 
 def run_reference(args):
@@ -105,14 +137,14 @@ def run_reference(args):
     arm.close()
     total_t = sum(dt for _, dt in rates)
     value = per_step * len(rates) / total_t
-    sample = (f'{per_step} domains per step, L~U{{{LMIN}..{LMAX}}}, {LAYERS}x{D} fp32, oracle port of '
-              f'reference fingerprint.py quantize under multiprocessing.Pool({cores})')
+    sample = (f'each step = {per_step} domains of the workload (L~U{{{LMIN}..{LMAX}}}, {LAYERS}x{D} fp32), {arm.what()} '
+              f'under multiprocessing.Pool({cores})')
     line = {
         'impl': 'reference', 'metric': 'domain fingerprints/s', 'value': value, 'unit': 'fingerprints/s',
         'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': total_t / len(rates) * 1e3,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-        'config': {'workload': workload_name(args.batch), 'sample': sample},
-        'cpu_baseline': {'value': value, 'unit': 'fingerprints/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+        'config': primary_config(args.batch, args.pool, max(1, args.gpus)),
+        'cpu_baseline': {'value': value, 'unit': 'fingerprints/s', 'cores': cores, 'kind': arm.kind, 'sample': sample},
         'e2e': {'value': value, 'unit': 'fingerprints/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }
     print(json.dumps(line), flush=True)
@@ -364,18 +396,16 @@ def run_ours(args):
         arm.close()
         if search_1m is not None:
             search_1m['cpu_baseline'] = cpu_search_rate(cores)
-        cpu = {'value': r, 'unit': 'fingerprints/s', 'cores': cores, 'kind': 'port', 'seconds': dt,
-               'sample': f'{n} domains, L~U{{{LMIN}..{LMAX}}}, {LAYERS}x{D} fp32: oracle port of reference '
-                         f'fingerprint.py quantize under multiprocessing.Pool({cores}) (embeddings pre-forked, not pickled)'}
+        cpu = {'value': r, 'unit': 'fingerprints/s', 'cores': cores, 'kind': arm.kind, 'seconds': dt,
+               'sample': f'{n} domains, L~U{{{LMIN}..{LMAX}}}, {LAYERS}x{D} fp32: {arm.what()} under '
+                         f'multiprocessing.Pool({cores}) (embeddings pre-forked, not pickled)'}
 
     if rank == 0:
         line = {
             'metric': 'domain fingerprints/s', 'value': value, 'unit': 'fingerprints/s', 'n_gpus': world,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': total_ms / args.steps,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': workload_name(B), 'domains_per_step': B, 'resident_batches': len(pool),
-                       'l2': 'inputs larger than L2 (each step streams ~%.1f GB)' % (sum(algo) / len(algo) / 1e9),
-                       'parallelism': f'domains sharded over {world} rank(s), no collective'},
+            'config': primary_config(B, len(pool), world),
             'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches, 'roofline': roofline, 'cpu_baseline': cpu,
             'protein_batch': fused, 'long_sequences': longseq, 'search': search, 'search_1m': search_1m,
             'search_allvsall': allvsall, 'search_stream': stream,
