@@ -14,6 +14,7 @@ LIB_PATH = os.environ.get('DCTD_LIB') or os.path.join(_HERE, 'libdctd.so')   # D
 OK = 0
 ERR_ARG, ERR_CUDA, ERR_WORKSPACE, ERR_UNSUPPORTED, ERR_NOMEM = -1, -2, -3, -4, -5
 FP_TABLES_RESIDENT = 1
+FP_PLAN_NO_FUSION, FP_PLAN_GENERAL_KERNEL, FP_PLAN_LONGEST_FIRST = 1, 2, 4
 L1_HEAP_ONLY = 1
 
 
@@ -63,13 +64,13 @@ def lib():
         'dctd_h2d_rows': (C.c_int, [vp, vp, i64, vp, vp, vp]),
         'dctd_h2d_gather': (C.c_int, [vp, i64, vp]),
         'dctd_fp_plan_create': (C.c_int, [C.POINTER(FpGeometry), C.POINTER(vp)]),
+        'dctd_fp_plan_create_ex': (C.c_int, [C.POINTER(FpGeometry), u32, C.POINTER(vp)]),
         'dctd_fp_plan_destroy': (None, [vp]),
         'dctd_fp_workspace_bytes': (sz, [vp]),
         'dctd_fp_algorithmic_bytes': (i64, [vp]),
         'dctd_fp_num_items': (i32, [vp]),
         'dctd_fp_execute': (C.c_int, [vp, vp, i64, vp, i64, vp, sz, u32, vp]),
         'dctd_fp_set_variant': (C.c_int, [C.c_int]),
-        'dctd_fp_set_fusion': (C.c_int, [C.c_int]),
         'dctd_fp_timing_read': (C.c_int, [vp, vp, vp]),
         'dctd_fp_plan_dump': (C.c_int, [vp, vp, i64, vp, i64, C.POINTER(i64), C.POINTER(i64)]),
         'dctd_fp_plan_dump_records': (C.c_int, [vp, vp, i64]),
@@ -90,8 +91,7 @@ def lib():
         'dctd_l1_keys_merge': (C.c_int, [vp, i32, i64, i32, vp, vp, vp, vp]),
         'dctd_l1_pair_scores': (C.c_int, [vp, i32, vp, vp, vp, i64, vp, vp, vp]),
     }
-    hooks = {'dctd_fp_set_variant', 'dctd_fp_set_fusion', 'dctd_fp_timing_read', 'dctd_fp_plan_dump', 'dctd_fp_plan_dump_records',
-             'dctd_l1_set_mode', 'dctd_l1_stream_stamps'}
+    hooks = {'dctd_fp_set_variant', 'dctd_fp_timing_read', 'dctd_l1_set_mode', 'dctd_l1_stream_stamps'}   # tuning builds only
     for name, (res, args) in sig.items():
         try:
             fn = getattr(L, name)      # AttributeError here = header / library mismatch

@@ -113,6 +113,7 @@ struct dctd_fp_plan {
     std::vector<Item> items;
     std::vector<int32_t> wsitems;   // 32 words per item (fp_ws_kernel.cuh), same order as items
     bool has_rider;           // some items carry their protein's global fingerprint along
+    uint32_t flags;           // DCTD_FP_PLAN_* options the plan was created with
     int32_t n_counters;       // 1 (work queue) + split arrival counters
     int64_t n_slabs;          // partial-sum slabs of (n-1)*D doubles
     int64_t algo_bytes;
@@ -795,9 +796,48 @@ __global__ void __launch_bounds__(MAXT, MINB) fp_kernel(const Params p) {
 // ------------------------------------------------------------------------------------------
 // host: layout, planner, launch
 // ------------------------------------------------------------------------------------------
-int g_variant = 0;   // tuning hook, see dctd_fp_set_variant
-int g_fuse = 1;      // protein-level fusion of the global fingerprint (dctd_fp_set_fusion)
-int g_ws_stages = 0; // tuning hook: cap on the TMA ring stages of the warp-specialised kernel (0 = as many as fit)
+#ifdef DCTD_TUNING
+// process-global A/B switches: tuning builds only (libdctd_tuning.so, dctd_fp_set_variant).  The release library has
+// no mutable global state: per-plan options travel in the flags of dctd_fp_plan_create_ex.
+int g_variant = 0;
+int g_ws_stages = 0; // cap on the TMA ring stages of the warp-specialised kernel (0 = as many as fit)
+#else
+constexpr int g_variant = 0;
+constexpr int g_ws_stages = 0;
+#endif
+
+// Queue order of the items.  The persistent CTAs pull items from one atomic queue.  Longest first (LPT) balances the
+// tail, but it also makes every CTA stream long items at the start of the launch (HBM-bound, finisher warps idle) and
+// short ones at its end (finisher-bound: an item's passes 2 cost ~19 k cycles whatever its length, HBM idle).  So the
+// short items - fewer rows than the finishers need to keep up, ~480 KB of input - are spread evenly, by rows, over the
+// long ones, which stay in descending order; the last long items (just above the balance length) carry no short ones
+// and even out the tail.
+void spread_short_items(std::vector<Item> &items, int D) {
+    const int balance = std::max(8, 491520 / (D * 4));
+    auto len = [](const Item &a) { return a.r1 - a.r0; };
+    size_t nb = 0;
+    while (nb < items.size() && len(items[nb]) >= balance) ++nb;       // items are sorted longest first
+    const size_t ns = items.size() - nb;
+    if (nb == 0 || ns == 0) return;
+    const size_t reserve = std::min<size_t>(nb / 8, 296);
+    int64_t rows_big = 0;
+    for (size_t i = 0; i + reserve < nb; ++i) rows_big += len(items[i]);
+    std::vector<Item> out;
+    out.reserve(items.size());
+    size_t j = 0;
+    int64_t cum = 0;
+    for (size_t i = 0; i < nb; ++i) {
+        out.push_back(items[i]);
+        if (i + reserve >= nb) continue;
+        cum += len(items[i]);
+        // short item j is due once (j + 0.5) / ns of the long rows have been queued
+        while (j < ns && (2 * (int64_t)j + 1) * rows_big <= 2 * cum * (int64_t)ns) out.push_back(items[nb + j++]);
+        if (i + reserve + 1 == nb)
+            while (j < ns) out.push_back(items[nb + j++]);
+    }
+    while (j < ns) out.push_back(items[nb + j++]);
+    items.swap(out);
+}
 
 Layout make_layout(int D, int n, int m, bool vec4, bool rider) {
     Layout l{};
@@ -919,8 +959,13 @@ int launch_ws(const dctd_fp_plan *plan, Params &prm, int max_smem, int n_sm, cud
 extern "C" {
 
 int dctd_fp_plan_create(const dctd_fp_geometry *geo, dctd_fp_plan **out_plan) {
+    return dctd_fp_plan_create_ex(geo, 0u, out_plan);
+}
+
+int dctd_fp_plan_create_ex(const dctd_fp_geometry *geo, uint32_t flags, dctd_fp_plan **out_plan) {
     if (!geo || !out_plan) return DCTD_ERR_ARG;
     *out_plan = nullptr;
+    if (flags & ~(DCTD_FP_PLAN_NO_FUSION | DCTD_FP_PLAN_GENERAL_KERNEL | DCTD_FP_PLAN_LONGEST_FIRST)) return DCTD_ERR_ARG;
     if (geo->n_layers < 1 || geo->D < 1 || geo->n < 2 || geo->n > kMaxN || geo->m < 2 ||
         geo->m > kMaxM || geo->m > geo->D || geo->n_src < 0 || geo->n_prot < 0 || geo->n_dom < 0)
         return DCTD_ERR_ARG;
@@ -932,6 +977,7 @@ int dctd_fp_plan_create(const dctd_fp_geometry *geo, dctd_fp_plan **out_plan) {
     if (!pl) return DCTD_ERR_NOMEM;
     pl->n_layers = geo->n_layers; pl->D = geo->D; pl->n = geo->n; pl->m = geo->m;
     pl->n_src = geo->n_src; pl->n_dom = geo->n_dom;
+    pl->flags = flags;
     pl->blob = nullptr; pl->blob_pinned = false; pl->blob_bytes = 0;
     pl->algo_bytes = 0;
     int rc = DCTD_OK;
@@ -1010,7 +1056,7 @@ int dctd_fp_plan_create(const dctd_fp_geometry *geo, dctd_fp_plan **out_plan) {
         std::vector<int32_t> global_of((size_t)geo->n_prot, -1);   // fused proteins: index of the global domain
         std::vector<std::vector<std::pair<int64_t, int64_t>>> filler((size_t)geo->n_prot);
         std::vector<std::vector<int32_t>> by_prot((size_t)geo->n_prot);
-        if (rc == DCTD_OK && g_fuse && geo->n <= 4) {      // rider kernels are built for n <= 4 (2n - 2 projections)
+        if (rc == DCTD_OK && !(flags & DCTD_FP_PLAN_NO_FUSION) && geo->n <= 4) {      // rider kernels are built for n <= 4 (2n - 2 projections)
             for (int i = 0; i < geo->n_dom; ++i) by_prot[geo->dom_prot[i]].push_back(i);
             for (int p = 0; p < geo->n_prot; ++p) {
                 int gdom = -1;
@@ -1135,6 +1181,7 @@ int dctd_fp_plan_create(const dctd_fp_geometry *geo, dctd_fp_plan **out_plan) {
             std::stable_sort(pl->items.begin(), pl->items.end(), [](const Item &a, const Item &b) {
                 return (a.r1 - a.r0) > (b.r1 - b.r0);
             });
+            if (!(flags & DCTD_FP_PLAN_LONGEST_FIRST)) spread_short_items(pl->items, geo->D);
             pl->n_counters = n_counters;
             pl->n_slabs = n_slabs;
             // fat item records of the warp-specialised kernel: everything its producer / finisher warps need
@@ -1241,12 +1288,14 @@ size_t dctd_fp_workspace_bytes(const dctd_fp_plan *plan) { return plan ? plan->t
 int64_t dctd_fp_algorithmic_bytes(const dctd_fp_plan *plan) { return plan ? plan->algo_bytes : 0; }
 int32_t dctd_fp_num_items(const dctd_fp_plan *plan) { return plan ? (int32_t)plan->items.size() : 0; }
 
-/* tuning hook (not in dctd.h): selects the pass-1 unroll / occupancy variant for n == 3 */
+#ifdef DCTD_TUNING
+/* tuning builds only (not in dctd.h): selects the pass-1 unroll / occupancy variant for n == 3 */
 int dctd_fp_set_variant(int v) {
     if (v >= 100) { g_ws_stages = v - 100; return DCTD_OK; }   // 100 + s: cap the TMA ring at s stages (100: no cap)
     g_variant = v;
     return DCTD_OK;
 }
+#endif
 
 /* DCTD_FP_TIMING builds: copies the 16 per-phase cycle counters of the last dctd_fp_execute on this
  * workspace to the host (synchronises the device) */
@@ -1262,10 +1311,7 @@ int dctd_fp_timing_read(const dctd_fp_plan *plan, const void *d_workspace, int64
 #endif
 }
 
-/* switch the protein-level fusion (global fingerprint riding on the domain items) on/off; default on */
-int dctd_fp_set_fusion(int on) { g_fuse = on ? 1 : 0; return DCTD_OK; }
-
-/* test hook: copies the plan's pieces (8 int32 each) / items (8 int32 each) to host buffers */
+/* introspection: copies the plan's pieces (8 int32 each) / items (8 int32 each) to host buffers */
 int dctd_fp_plan_dump(const dctd_fp_plan *plan, int32_t *pieces, int64_t max_pieces, int32_t *items,
                       int64_t max_items, int64_t *n_pieces, int64_t *n_items) {
     if (!plan) return DCTD_ERR_ARG;
@@ -1276,7 +1322,7 @@ int dctd_fp_plan_dump(const dctd_fp_plan *plan, int32_t *pieces, int64_t max_pie
     return DCTD_OK;
 }
 
-/* test hook: copies the 32-word item records of the warp-specialised kernel (same order as the items) */
+/* introspection: copies the 32-word item records of the warp-specialised kernel (same order as the items) */
 int dctd_fp_plan_dump_records(const dctd_fp_plan *plan, int32_t *records, int64_t max_items) {
     if (!plan || !records || max_items < 0) return DCTD_ERR_ARG;
     const size_t n = std::min<size_t>((size_t)max_items, plan->items.size());
@@ -1342,7 +1388,8 @@ int dctd_fp_execute(const dctd_fp_plan *plan, const void *const *h_src_ptrs, int
     const int K = plan->n - 1;
     // The reference's configuration (n = 3; ESM-2 t33 / t30 widths, contiguous rows) runs on the warp-specialised
     // TMA kernel; every other shape on the general kernel below.  g_variant == 9 forces the general kernel (A/B runs).
-    if (vec4 && ld == plan->D && K == 2 && g_variant != 9 && (plan->D == 1280 || plan->D == 640)) {
+    if (vec4 && ld == plan->D && K == 2 && g_variant != 9 && !(plan->flags & DCTD_FP_PLAN_GENERAL_KERNEL) &&
+        (plan->D == 1280 || plan->D == 640)) {
         bool launched = false;
         int rc;
         if (plan->D == 1280)

@@ -90,10 +90,10 @@ def parse_domain(dom: str, n_rows: int):
 class _Plan:
     """Owns a dctd_fp_plan handle."""
 
-    def __init__(self, geo: _lib.FpGeometry, keep):
+    def __init__(self, geo: _lib.FpGeometry, keep, flags: int = 0):
         self._keep = keep
         self.handle = C.c_void_p()
-        _lib.check(_lib.lib().dctd_fp_plan_create(C.byref(geo), C.byref(self.handle)), 'dctd_fp_plan_create')
+        _lib.check(_lib.lib().dctd_fp_plan_create_ex(C.byref(geo), int(flags), C.byref(self.handle)), 'dctd_fp_plan_create')
         L = _lib.lib()
         self.workspace_bytes = int(L.dctd_fp_workspace_bytes(self.handle))
         self.algorithmic_bytes = int(L.dctd_fp_algorithmic_bytes(self.handle))
@@ -110,8 +110,8 @@ def _i32(a):
 
 
 def make_plan(n_layers, D, n, m, src_rows, prot_src0, prot_nsrc, dom_prot, dom_seg_off, seg_beg, seg_end,
-              maxlen=DEFAULT_MAXLEN, overlap=OVERLAP) -> _Plan:
-    """Host-side work decomposition for one batch (dctd_fp_plan_create)."""
+              maxlen=DEFAULT_MAXLEN, overlap=OVERLAP, flags: int = 0) -> _Plan:
+    """Host-side work decomposition for one batch (dctd_fp_plan_create_ex; ``flags``: _lib.FP_PLAN_*)."""
     arrs = [_i32(x) for x in (src_rows, prot_src0, prot_nsrc, dom_prot, dom_seg_off, seg_beg, seg_end)]
     geo = _lib.FpGeometry()
     geo.n_layers, geo.D, geo.n, geo.m = int(n_layers), int(D), int(n), int(m)
@@ -120,7 +120,7 @@ def make_plan(n_layers, D, n, m, src_rows, prot_src0, prot_nsrc, dom_prot, dom_s
     geo.n_prot, geo.prot_src0, geo.prot_nsrc = len(arrs[1]), arrs[1].ctypes.data, arrs[2].ctypes.data
     geo.n_dom, geo.dom_prot, geo.dom_seg_off = len(arrs[3]), arrs[3].ctypes.data, arrs[4].ctypes.data
     geo.seg_beg, geo.seg_end = arrs[5].ctypes.data, arrs[6].ctypes.data
-    return _Plan(geo, arrs)
+    return _Plan(geo, arrs, flags)
 
 
 def execute_plan(plan: _Plan, src_tensors, out: torch.Tensor, tables_resident=False, workspace=None):
@@ -189,14 +189,15 @@ def _stage_buffer(device, nbytes):
     return buf
 
 
-def quantize_batch(fps, qdim=(3, 80, 3, 80), device=None, maxlen=DEFAULT_MAXLEN, overlap=OVERLAP, _timing=None):
+def quantize_batch(fps, qdim=(3, 80, 3, 80), device=None, maxlen=DEFAULT_MAXLEN, overlap=OVERLAP, plan_flags: int = 0,
+                   _timing=None):
     """``quantize`` for a list of Fingerprint-like objects in one kernel launch per (n, m) group.
 
     Each object needs ``embed`` ({layer: [L, D] array | list of window arrays}), ``domains`` (list of
     RecCut strings) and ``quants`` (dict); they are updated exactly as the reference ``quantize`` does
     (src/fingerprint.py:184-201).  Host embeddings (numpy, CPU torch, pinned or not) are staged into one
     device buffer with a single C call (one cudaMemcpyAsync per array); CUDA tensors are read in place.
-    Returns the list for convenience.
+    ``plan_flags``: per-call options of the work decomposition (``_lib.FP_PLAN_NO_FUSION`` ...).  Returns the list.
     """
     fps = list(fps)
     if not fps:
@@ -354,7 +355,7 @@ def quantize_batch(fps, qdim=(3, 80, 3, 80), device=None, maxlen=DEFAULT_MAXLEN,
         outs = []
         for (n, m), lids in groups.items():
             plan = make_plan(len(lids), D, n, m, src_rows, prot_src0, prot_nsrc, dom_prot, dom_seg_off,
-                             seg_beg, seg_end, maxlen, overlap)
+                             seg_beg, seg_end, maxlen, overlap, plan_flags)
             out = torch.empty((len(dom_prot), len(lids) * n * m), dtype=torch.int8, device=dev)
             ptrs = np.array([v for li in lids for v in ptr[li]], dtype=np.uint64)
             ws = _workspace(dev, plan.workspace_bytes)

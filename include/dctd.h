@@ -11,9 +11,9 @@
  *     named h_* / "host" are host pointers; the caller owns every buffer including workspaces;
  *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); all device work
  *     is stream-ordered on it and the functions do not synchronise unless stated;
- *   - the library keeps no global mutable state besides a thread-local "last CUDA error" and launch counter.
- *     (The tuning / test hooks that are NOT declared here - dctd_fp_set_variant, dctd_fp_set_fusion, dctd_l1_set_mode,
- *     dctd_fp_plan_dump*, dctd_fp_timing_read - flip process-global switches; they exist for A/B runs and tests only.)
+ *   - the library keeps no global mutable state besides a thread-local "last CUDA error" and launch counter: options
+ *     are per plan / per call (flags).  The A/B switches used while tuning (dctd_fp_set_variant, dctd_l1_set_mode) exist
+ *     only in the separate tuning build (make -C dctdomain_b200/csrc tuning), not in libdctd.so.
  */
 #ifndef DCTD_H
 #define DCTD_H
@@ -97,8 +97,16 @@ typedef struct dctd_fp_geometry {
     const int32_t *seg_end;     /* host [n_seg] exclusive end row (already clipped to the protein) */
 } dctd_fp_geometry;
 
-/* Builds the work decomposition (pieces, split items sorted longest first).  Host only. */
+/* Builds the work decomposition (pieces; items of at most 512 rows in queue order: long items longest first with the
+ * short ones spread evenly between them).  Host only. */
 int dctd_fp_plan_create(const dctd_fp_geometry *geo, dctd_fp_plan **out_plan);
+/* The same with per-plan options (0 = dctd_fp_plan_create): */
+#define DCTD_FP_PLAN_NO_FUSION 1u      /* do not let a protein's global fingerprint ride on its other domains' items
+                                          (every domain then reads its own rows, as the reference does) */
+#define DCTD_FP_PLAN_GENERAL_KERNEL 2u /* run on the general kernel even where the warp-specialised TMA kernel applies
+                                          (cross-check of the two: results agree to <= 1 LSB on a handful of bytes) */
+#define DCTD_FP_PLAN_LONGEST_FIRST 4u  /* plain longest-first queue order */
+int dctd_fp_plan_create_ex(const dctd_fp_geometry *geo, uint32_t flags, dctd_fp_plan **out_plan);
 void dctd_fp_plan_destroy(dctd_fp_plan *plan);
 /* bytes of device workspace dctd_fp_execute needs for this plan */
 size_t dctd_fp_workspace_bytes(const dctd_fp_plan *plan);
@@ -106,6 +114,11 @@ size_t dctd_fp_workspace_bytes(const dctd_fp_plan *plan);
  * domain once (rows shared with a riding global fingerprint once, rows averaged from two windows twice) */
 int64_t dctd_fp_algorithmic_bytes(const dctd_fp_plan *plan);
 int32_t dctd_fp_num_items(const dctd_fp_plan *plan);
+/* introspection (tests): the plan's pieces and items as 8 int32 each, and the 32-word item records of the
+ * warp-specialised kernel, in queue order; counts through n_pieces / n_items (either may be NULL) */
+int dctd_fp_plan_dump(const dctd_fp_plan *plan, int32_t *pieces, int64_t max_pieces, int32_t *items, int64_t max_items,
+                      int64_t *n_pieces, int64_t *n_items);
+int dctd_fp_plan_dump_records(const dctd_fp_plan *plan, int32_t *records, int64_t max_items);
 
 #define DCTD_FP_TABLES_RESIDENT 1u /* the plan tables were already uploaded to this workspace by an
                                       earlier dctd_fp_execute with the same plan: skip the copy */

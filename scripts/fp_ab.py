@@ -1,9 +1,10 @@
-"""A/B run (GPU box): general fingerprint kernel (variant 9) against the warp-specialised TMA kernel (variant 0),
-alternating inside one process, on three workloads: configs[1]-shaped independent domains at D = 1280 and 640, and a
-protein-shaped batch (4 domains + the riding global fingerprint).  Reports GB/s of algorithmic bytes and how many
-output bytes differ between the two kernels.
+"""A/B run (GPU box): general fingerprint kernel against the warp-specialised TMA kernel with the plain longest-first
+queue order and with the short items spread (the default), alternating inside one process, on five workloads:
+configs[1]-shaped independent domains at D = 1280 and 640, a protein-shaped batch (4 domains + the riding global
+fingerprint), short domains, and long proteins as windows.  Reports GB/s of algorithmic bytes and how many output
+bytes differ from the first variant.
 
-    python scripts/fp_ab.py [n_dom] [ring-stage caps, e.g. 0,5,3]
+    python scripts/fp_ab.py [n_dom]
 """
 import json
 import os
@@ -20,23 +21,28 @@ L = _lib.lib()
 
 
 def timed(plan, srcs, out, iters=10):
+    ws = torch.empty(max(plan.workspace_bytes, 256), dtype=torch.uint8, device='cuda')
     for _ in range(3):
-        execute_plan(plan, srcs, out)
+        execute_plan(plan, srcs, out, workspace=ws)
     torch.cuda.synchronize()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
     ev[0].record()
     for _ in range(iters):
-        execute_plan(plan, srcs, out, tables_resident=True)
+        execute_plan(plan, srcs, out, tables_resident=True, workspace=ws)
     ev[1].record()
     torch.cuda.synchronize()
     return ev[0].elapsed_time(ev[1]) / iters
 
 
-def ab(name, plan, srcs, out, unique_bytes, variants, res):
+def ab(name, mk, srcs, out, unique_bytes, variants, res):
     ref = None
-    for label, var, stages in variants:
-        L.dctd_fp_set_variant(var)
-        L.dctd_fp_set_variant(100 + stages)
+    plans = {}
+    for label, flags in variants:
+        if flags not in plans:
+            plans[flags] = mk(flags)
+        plan = plans[flags]
+        if unique_bytes is None:
+            unique_bytes = plan.algorithmic_bytes
         ms = timed(plan, srcs, out)
         o = out.cpu().numpy().copy()
         if ref is None:
@@ -47,8 +53,6 @@ def ab(name, plan, srcs, out, unique_bytes, variants, res):
                  bytes_differing_from_first=diff, max_abs_diff=maxd)
         res.setdefault(name, {}).setdefault(label, []).append(r)
         print(name, label, r, flush=True)
-    L.dctd_fp_set_variant(0)
-    L.dctd_fp_set_variant(100)
 
 
 def domains(n_dom, D, variants, res, lo=40, hi=500):
@@ -58,9 +62,9 @@ def domains(n_dom, D, variants, res, lo=40, hi=500):
     total = int(off[-1])
     torch.manual_seed(0)
     layers = [torch.randn(total, D, device='cuda') for _ in range(2)]
-    plan = make_plan(2, D, 3, 80, [total], [0], [1], [0] * n_dom, list(range(n_dom + 1)), off[:-1], off[1:])
+    mk = lambda fl: make_plan(2, D, 3, 80, [total], [0], [1], [0] * n_dom, list(range(n_dom + 1)), off[:-1], off[1:], flags=fl)
     out = torch.empty((n_dom, 480), dtype=torch.int8, device='cuda')
-    ab(f'domains_{n_dom}x{D}_L{lo}-{hi}', plan, [[layers[0]], [layers[1]]], out, plan.algorithmic_bytes, variants, res)
+    ab(f'domains_{n_dom}x{D}_L{lo}-{hi}', mk, [[layers[0]], [layers[1]]], out, None, variants, res)
 
 
 def proteins(n_prot, D, variants, res):
@@ -79,9 +83,9 @@ def proteins(n_prot, D, variants, res):
         dom_prot.append(p); sb.append(0); se.append(int(Lp))
     nd = len(dom_prot)
     srcs = [[layers[l][poff[p]:poff[p + 1]] for p in range(n_prot)] for l in range(2)]
-    plan = make_plan(2, D, 3, 80, plens, list(range(n_prot)), [1] * n_prot, dom_prot, list(range(nd + 1)), sb, se)
+    mk = lambda fl: make_plan(2, D, 3, 80, plens, list(range(n_prot)), [1] * n_prot, dom_prot, list(range(nd + 1)), sb, se, flags=fl)
     out = torch.empty((nd, 480), dtype=torch.int8, device='cuda')
-    ab(f'proteins_{n_prot}x{D}_fused', plan, srcs, out, 2 * total * D * 4, variants, res)
+    ab(f'proteins_{n_prot}x{D}_fused', mk, srcs, out, 2 * total * D * 4, variants, res)
 
 
 def windows(n_prot, D, variants, res, maxlen=500, overlap=200):
@@ -121,16 +125,15 @@ def windows(n_prot, D, variants, res, maxlen=500, overlap=200):
             dom_prot.append(p); sb.append(a); se.append(b)
         dom_prot.append(p); sb.append(0); se.append(int(Lp))
     nd = len(dom_prot)
-    plan = make_plan(2, D, 3, 80, src_rows, prot_src0, prot_nsrc, dom_prot, list(range(nd + 1)), sb, se,
-                     maxlen=maxlen, overlap=overlap)
+    mk = lambda fl: make_plan(2, D, 3, 80, src_rows, prot_src0, prot_nsrc, dom_prot, list(range(nd + 1)), sb, se,
+                              maxlen=maxlen, overlap=overlap, flags=fl)
     out = torch.empty((nd, 480), dtype=torch.int8, device='cuda')
-    ab(f'windows_{n_prot}x{D}_L501-4000', plan, srcs, out, 2 * total * D * 4, variants, res)
+    ab(f'windows_{n_prot}x{D}_L501-4000', mk, srcs, out, 2 * total * D * 4, variants, res)
 
 
 def main():
     n_dom = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
-    caps = [int(v) for v in sys.argv[2].split(',')] if len(sys.argv) > 2 else [0]
-    variants = [('general', 9, 0)] + [(f'ws_stages{c or "max"}', 0, c) for c in caps]
+    variants = [('general', _lib.FP_PLAN_GENERAL_KERNEL), ('ws_longest_first', _lib.FP_PLAN_LONGEST_FIRST), ('ws_spread', 0)]
     variants = variants + variants
     res = {}
     domains(n_dom, 1280, variants, res)

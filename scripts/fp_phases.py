@@ -18,17 +18,17 @@ WS_NAMES = ['prod_wait_free_stage', 'prod_total', 'cons_wait_full_stage', 'cons_
             'fin_total', 'fin_stage1', 'fin_pass2a', 'fin_out', 'items', 'fin_reduce', 'fin_pass2b']
 
 
-def run(name, plan, srcs, out):
+def run(name, mk, srcs, out):
     res = {}
-    for label, variant in (('general', 9), ('ws', 0)):
-        _lib.lib().dctd_fp_set_variant(variant)
+    for label, flags in (('general', _lib.FP_PLAN_GENERAL_KERNEL), ('ws_longest_first', _lib.FP_PLAN_LONGEST_FIRST), ('ws', 0)):
+        plan = mk(flags)
         ws = torch.empty(plan.workspace_bytes, dtype=torch.uint8, device='cuda')
         for _ in range(3):
             execute_plan(plan, srcs, out, workspace=ws)
         torch.cuda.synchronize()
         buf = np.zeros(16, dtype=np.int64)
         _lib.check(_lib.lib().dctd_fp_timing_read(plan.handle, ws.data_ptr(), buf.ctypes.data))
-        if variant == 9:
+        if label == 'general':
             tot = buf[[0, 1, 2, 3, 4, 5, 6]].sum()
             rep = {n: round(float(v) / tot, 4) for n, v in zip(NAMES, buf) if n != '-'}
             rep['cycles_per_item'] = float(tot) / plan.n_items
@@ -43,7 +43,6 @@ def run(name, plan, srcs, out):
                                           (('stage1', 7), ('pass2a', 8), ('reduce', 11), ('pass2b', 12), ('minmax_out', 9))}
         print(name, label, json.dumps(rep), flush=True)
         res[label] = rep
-    _lib.lib().dctd_fp_set_variant(0)
     return res
 
 
@@ -56,9 +55,9 @@ def main():
     lens = rs.randint(40, 501, size=n_dom)
     off = np.concatenate([[0], np.cumsum(lens)])
     layers = [torch.randn(int(off[-1]), D, device='cuda') for _ in range(2)]
-    plan = make_plan(2, D, 3, 80, [int(off[-1])], [0], [1], [0] * n_dom, list(range(n_dom + 1)), off[:-1], off[1:])
+    mk = lambda fl: make_plan(2, D, 3, 80, [int(off[-1])], [0], [1], [0] * n_dom, list(range(n_dom + 1)), off[:-1], off[1:], flags=fl)
     out = torch.empty((n_dom, 480), dtype=torch.int8, device='cuda')
-    res = {'domains': run('domains', plan, [[layers[0]], [layers[1]]], out)}
+    res = {'domains': run('domains', mk, [[layers[0]], [layers[1]]], out)}
     # protein-shaped batch (fused)
     n_prot = 1024
     plens = rs.randint(200, 1001, size=n_prot)
@@ -73,9 +72,9 @@ def main():
         dom_prot.append(p); sb.append(0); se.append(int(L))
     nd = len(dom_prot)
     srcs = [[layers[l][poff[p]:poff[p + 1]] for p in range(n_prot)] for l in range(2)]
-    plan = make_plan(2, D, 3, 80, plens, list(range(n_prot)), [1] * n_prot, dom_prot, list(range(nd + 1)), sb, se)
+    mk = lambda fl: make_plan(2, D, 3, 80, plens, list(range(n_prot)), [1] * n_prot, dom_prot, list(range(nd + 1)), sb, se, flags=fl)
     out = torch.empty((nd, 480), dtype=torch.int8, device='cuda')
-    res['proteins_fused'] = run('proteins_fused', plan, srcs, out)
+    res['proteins_fused'] = run('proteins_fused', mk, srcs, out)
     os.makedirs('gpurun_out', exist_ok=True)
     json.dump(res, open('gpurun_out/fp_phases.json', 'w'), indent=1)
 

@@ -242,11 +242,7 @@ def test_protein_level_fusion_on_and_off():
     quantize_batch(fused, [3, 80, 3, 80])
     rs = np.random.RandomState(21)
     plain = batch()
-    _lib.lib().dctd_fp_set_fusion(0)
-    try:
-        quantize_batch(plain, [3, 80, 3, 80])
-    finally:
-        _lib.lib().dctd_fp_set_fusion(1)
+    quantize_batch(plain, [3, 80, 3, 80], plan_flags=_lib.FP_PLAN_NO_FUSION)
     for a, b in zip(fused, plain):
         assert a.domains == b.domains
         emb = {lay: (fo.stitch_chunks(v) if isinstance(v, list) else v) for lay, v in a.embed.items()}
@@ -263,7 +259,7 @@ def test_protein_level_fusion_on_and_off():
 def test_geometry_fuzz_warp_specialised_vs_general_kernel(seed, D):
     """Random batch geometry - short and long proteins, maxlen windows, discontinuous / overlapping / unsorted
     domains, global domains with and without fusion partners, domains long enough to be split over items - run through
-    the warp-specialised kernel and the general one (dctd_fp_set_variant(9)).  The two differ only in float32 chain
+    the warp-specialised kernel and the general one (DCTD_FP_PLAN_GENERAL_KERNEL).  The two differ only in float32 chain
     lengths: at most 1 LSB on a handful of bytes; and each kernel is bit-reproducible from launch to launch (its
     summation orders are fixed, whatever the scheduling of the persistent CTAs)."""
     from dctdomain_b200 import _lib
@@ -322,22 +318,21 @@ def test_geometry_fuzz_warp_specialised_vs_general_kernel(seed, D):
     layers = [torch.randn(total, D, generator=g, device='cuda') * (1 + l) + 3 * l for l in range(2)]
     off = np.concatenate([[0], np.cumsum(src_rows)])
     srcs = [[layers[l][off[i]:off[i + 1]] for i in range(len(src_rows))] for l in range(2)]
-    plan = make_plan(2, D, 3, 80, src_rows, prot_src0, prot_nsrc, dom_prot, seg_off, sb, se, maxlen=maxlen, overlap=overlap)
     nd = len(dom_prot)
     outs = {}
-    L = _lib.lib()
-    try:
-        for variant in (9, 0):
-            L.dctd_fp_set_variant(variant)
-            runs = []
-            for _ in range(3):
-                out = torch.full((nd, 480), 77, dtype=torch.int8, device='cuda')
-                execute_plan(plan, srcs, out)
-                runs.append(out.cpu().numpy())
-            assert all(np.array_equal(runs[0], r) for r in runs[1:]), f'variant {variant} is not reproducible'
-            outs[variant] = runs[0].astype(int)
-    finally:
-        L.dctd_fp_set_variant(0)
+    # 9: the general kernel; 0: the warp-specialised kernel; 4: the same with the plain longest-first queue order - the
+    # queue order only changes which CTA does what when, never a result
+    for variant, flags in ((9, _lib.FP_PLAN_GENERAL_KERNEL), (0, 0), (4, _lib.FP_PLAN_LONGEST_FIRST)):
+        plan = make_plan(2, D, 3, 80, src_rows, prot_src0, prot_nsrc, dom_prot, seg_off, sb, se, maxlen=maxlen,
+                         overlap=overlap, flags=flags)
+        runs = []
+        for _ in range(3):
+            out = torch.full((nd, 480), 77, dtype=torch.int8, device='cuda')
+            execute_plan(plan, srcs, out)
+            runs.append(out.cpu().numpy())
+        assert all(np.array_equal(runs[0], r) for r in runs[1:]), f'variant {variant} is not reproducible'
+        outs[variant] = runs[0].astype(int)
+    assert np.array_equal(outs[0], outs[4])
     diff = np.abs(outs[0] - outs[9])
     assert diff.max() <= 1, np.argwhere(diff > 1)[:5]
     assert (diff != 0).mean() <= TOL_FRAC, (int((diff != 0).sum()), diff.size)

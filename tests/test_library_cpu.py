@@ -50,12 +50,9 @@ def test_planner_single_source(lib):
                                [0, 176, -1, 0, 124, 0, 176], [0, 0, -1, 0, 77, 124, 0]]
     assert len(items) == 4 and plan.algorithmic_bytes == 2 * 300 * 1280 * 4      # every row is read once
     assert items[0, 3] - items[0, 2] == 201 and items[0, 6] == 1                 # longest first; rider = domain 1
-    lib.dctd_fp_set_fusion(0)
-    try:
-        plan2 = _plan(lib, n_layers=2, D=1280, n=3, m=80, src_rows=[300], prot_src0=[0], prot_nsrc=[1],
-                      dom_prot=[0, 0], dom_seg_off=[0, 2, 3], seg_beg=[176, 0, 0], seg_end=[300, 77, 300])
-    finally:
-        lib.dctd_fp_set_fusion(1)
+    plan2 = _plan(lib, n_layers=2, D=1280, n=3, m=80, src_rows=[300], prot_src0=[0], prot_nsrc=[1],
+                  dom_prot=[0, 0], dom_seg_off=[0, 2, 3], seg_beg=[176, 0, 0], seg_end=[300, 77, 300],
+                  flags=_lib.FP_PLAN_NO_FUSION)
     pieces2, items2 = _dump(lib, plan2)
     assert pieces2[:, :6].tolist() == [[0, 176, -1, 0, 124, 0], [0, 0, -1, 0, 77, 124], [0, 0, -1, 0, 300, 0]]
     assert plan2.algorithmic_bytes == 2 * (201 + 300) * 1280 * 4 and (items2[:, 6] == -1).all()
@@ -298,3 +295,30 @@ def test_planner_fuzz_items_cover_every_domain_row_once(lib, seed):
     for (p, layer), rows in covered.items():
         assert sorted(rows) == list(range(plens[p])), (p, layer)
     assert len(covered) == n_layers * len({dom_prot[d] for d in rider_targets})
+
+
+def test_queue_order_spreads_short_items_and_keeps_every_item(lib):
+    """Queue order of the persistent kernel (csrc/fingerprint.cu:spread_short_items): long items stay longest first, the
+    short ones (< ~480 KB of input = 96 rows at D = 1280) are spread between them instead of piling up at the end of the
+    launch, the last long items carry none; DCTD_FP_PLAN_LONGEST_FIRST gives the plain order; both hold the same items."""
+    rs = np.random.RandomState(5)
+    lens = rs.randint(20, 600, size=3000)
+    off = np.concatenate([[0], np.cumsum(lens)])
+    kw = dict(n_layers=1, D=1280, n=3, m=80, src_rows=[int(off[-1])], prot_src0=[0], prot_nsrc=[1],
+              dom_prot=[0] * len(lens), dom_seg_off=list(range(len(lens) + 1)), seg_beg=off[:-1], seg_end=off[1:])
+    _, lpt = _dump(lib, _plan(lib, flags=_lib.FP_PLAN_LONGEST_FIRST, **kw))
+    _, mix = _dump(lib, _plan(lib, **kw))
+    rows = lambda it: it[:, 3] - it[:, 2]
+    assert (np.diff(rows(lpt)) <= 0).all()
+    assert sorted(map(tuple, lpt.tolist())) == sorted(map(tuple, mix.tolist()))          # a permutation
+    r = rows(mix)
+    long_, short = r[r >= 96], r[r < 96]
+    assert (np.diff(long_) <= 0).all() and (np.diff(short) <= 0).all() and len(short) > 100
+    pos = np.nonzero(r < 96)[0]
+    assert pos.max() < len(r) - 100                     # the tail is made of long items just above the balance length
+    # evenly spread by rows: the share of long rows queued before the j-th short item is ~ (j + 0.5) / n_short
+    cum_long = np.cumsum(np.where(r >= 96, r, 0))
+    total = cum_long[pos.max()]
+    frac = cum_long[pos] / total
+    want = (np.arange(len(pos)) + 0.5) / len(pos)
+    assert np.abs(frac - want).max() < 0.01

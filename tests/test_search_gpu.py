@@ -87,6 +87,7 @@ def test_add_in_pieces_and_roundtrip(tmp_path):
     assert idx.ntotal == 1000 and np.array_equal(idx.reconstruct_n(), db)
     _check(db[:30], db, 50, pieces=7)
     path = str(tmp_path / 'x.index')
+    idx = _index(db, metric_l1=False, pieces=7)   # the reference writes the IndexFlatL2 it built (src/database.py:241-243)
     dindex.write_index(idx, path)
     raw = open(path, 'rb').read()
     assert raw[:4] == b'IxF2' and len(raw) == 4 + 4 + 8 * 3 + 1 + 4 + 8 + 1000 * 480 * 4
