@@ -56,7 +56,14 @@ struct WsCfg {
     static constexpr int R = R0 < 2 ? 2 : (R0 > 8 ? 8 : R0);   // rows per stage (even)
     static constexpr int T = 32 * (1 + NCW + kWsFinWarps);
     static constexpr int STAGE_BYTES = R * DC * 4;
-    static constexpr int FLUSH_EVERY = (8 / R) < 1 ? 1 : (8 / R);
+#ifndef WS_FLUSH_ROWS
+#define WS_FLUSH_ROWS 8
+#endif
+#ifndef WS_FLUSH_ROWS_RIDER
+#define WS_FLUSH_ROWS_RIDER WS_FLUSH_ROWS
+#endif
+    static constexpr int FLUSH_ROWS = RIDER ? WS_FLUSH_ROWS_RIDER : WS_FLUSH_ROWS;   // float32 chain length of pass 1
+    static constexpr int FLUSH_EVERY = (FLUSH_ROWS / R) < 1 ? 1 : (FLUSH_ROWS / R);
     static_assert(DC % 128 == 0, "one consumer warp per 128 columns (and float4 steps over D/4 columns)");
     static_assert(R % 2 == 0, "dual stages hold R/2 rows of each window");
 };
@@ -307,6 +314,14 @@ __global__ void __launch_bounds__(WsCfg<K, DC, RIDER>::T, 1) fp_ws_kernel(const 
             }
             const unsigned int st = ring_u32 + (unsigned int)s * Cfg::STAGE_BYTES;
             const int bslot = mt.z >> 8;
+            // All R row slots of the stage are loaded before the stage's record is inspected: the loads only depend on
+            // the stage index, so their latency overlaps that of the record (slots beyond nrows hold stale rows, which
+            // nothing below uses).  The next stage index is computed here as well, off the critical path.
+            pk2 x0[R], x1[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r) lds_pk4(st + r * D * 4, x0[r], x1[r]);
+            const int s_cur = s;
+            if (++s == NST) { s = 0; fph ^= 1u; }
             if (nrows == R && !(flags & (kStDual | kStPivotOnly))) {
                 // the common stage: R rows of one source.  Straight-line code: every load is issued before the
                 // first use, and the stage goes back to the producer as soon as the loads have been performed
@@ -314,16 +329,14 @@ __global__ void __launch_bounds__(WsCfg<K, DC, RIDER>::T, 1) fp_ws_kernel(const 
                 // Without a rider all basis values are fetched up front as well (measured: +2 % at D = 1280, +6 % at
                 // D = 640); with a rider (twice the projections) that would spill, so they are fetched row by row.
                 constexpr int CR = RIDER ? 1 : R;
-                pk2 x0[R], x1[R], c[CR][KS];
-#pragma unroll
-                for (int r = 0; r < R; ++r) lds_pk4(st + r * D * 4, x0[r], x1[r]);
+                pk2 c[CR][KS];
                 if constexpr (!RIDER) {
 #pragma unroll
                     for (int r = 0; r < R; ++r)
                         load_basis<KS>(basis + (size_t)((bslot + r) & (kWsBasisRows - 1)) * KS, c[r]);
                 }
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&empty[s]);
+                if (lane == 0) mbar_arrive(&empty[s_cur]);
                 if (flags & kStPivotInline) {
                     npiv0 = mul2(x0[0], neg);
                     npiv1 = mul2(x1[0], neg);
@@ -340,23 +353,11 @@ __global__ void __launch_bounds__(WsCfg<K, DC, RIDER>::T, 1) fp_ws_kernel(const 
                 }
             } else {
                 // partial stages, rows averaged from two windows, pivot-only stages
-                pk2 x0[R], x1[R];
-#pragma unroll
-                for (int r = 0; r < R; ++r) { x0[r] = zero; x1[r] = zero; }
-                if (!(flags & kStDual)) {
-#pragma unroll
-                    for (int r = 0; r < R; ++r)
-                        if (r < nrows) lds_pk4(st + r * D * 4, x0[r], x1[r]);
-                } else {
+                if (flags & kStDual) {
 #pragma unroll
                     for (int r = 0; r < R / 2; ++r) {
-                        if (r < nrows) {
-                            pk2 y0, y1;
-                            lds_pk4(st + r * D * 4, x0[r], x1[r]);
-                            lds_pk4(st + (R / 2 + r) * D * 4, y0, y1);
-                            x0[r] = mul2(add2(x0[r], y0), hf);      // embedding.py:186: (prev + cur) / 2 in float32
-                            x1[r] = mul2(add2(x1[r], y1), hf);
-                        }
+                        x0[r] = mul2(add2(x0[r], x0[R / 2 + r]), hf);      // embedding.py:186: (prev + cur) / 2 in float32
+                        x1[r] = mul2(add2(x1[r], x1[R / 2 + r]), hf);
                     }
                 }
                 if (flags & (kStPivotOnly | kStPivotInline)) {
@@ -380,9 +381,8 @@ __global__ void __launch_bounds__(WsCfg<K, DC, RIDER>::T, 1) fp_ws_kernel(const 
                 }
                 // the stage's rows and basis are consumed: give it back to the producer
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&empty[s]);
+                if (lane == 0) mbar_arrive(&empty[s_cur]);
             }
-            if (++s == NST) { s = 0; fph ^= 1u; }
             if (flags & kStPivotOnly) continue;
             if (++nflush == Cfg::FLUSH_EVERY || (flags & kStLast)) {
                 nflush = 0;
@@ -415,7 +415,9 @@ __global__ void __launch_bounds__(WsCfg<K, DC, RIDER>::T, 1) fp_ws_kernel(const 
                             *reinterpret_cast<double2 *>(slab + k * D + col) = make_double2(acc[K + k][0], acc[K + k][1]);
                             *reinterpret_cast<double2 *>(slab + k * D + col + 2) = make_double2(acc[K + k][2], acc[K + k][3]);
                         }
-                        __threadfence();
+                        // no fence here: these stores reach the finishers through the u_full mbarrier (release / acquire
+                        // at CTA scope); the finisher thread that takes the rider ticket fences at GPU scope before its
+                        // atomicAdd, and that release is cumulative over everything ordered before it
                     }
                 }
                 if (ctid == 0) u_slot[ub] = mt.z & 255;
