@@ -76,9 +76,88 @@ __global__ void __launch_bounds__(256) gather_kernel(const dctd_copy_desc *__res
 int dctd_h2d_gather(const dctd_copy_desc *d_table, int64_t n, void *stream) {
     if (n < 0 || (n > 0 && !d_table)) return DCTD_ERR_ARG;
     if (n == 0) return DCTD_OK;
-    const int grid = (int)(n < 148 * 8 ? n : 148 * 8);
+    int dev = 0, n_sm = 0;
+    DCTD_CUDA_TRY(cudaGetDevice(&dev));
+    DCTD_CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+    const int grid = (int)(n < (int64_t)n_sm * 8 ? n : (int64_t)n_sm * 8);
     gather_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_table, (long long)n);
     DCTD_LAUNCH_CHECK();
+    return DCTD_OK;
+}
+
+/* RecCut domain strings -> segment arrays with get_doms' rules (reference src/fingerprint.py:160-171), for a whole
+ * batch in one call.  See dctd.h. */
+int dctd_parse_domains(const char *text, int64_t text_len, int32_t n_str, const int32_t *str_prot,
+                       const int32_t *prot_len, int32_t n_prot, int32_t *dom_str, int32_t *dom_seg_off,
+                       int32_t *seg_beg, int32_t *seg_end, int64_t max_segs, int32_t *n_dom_out,
+                       int32_t *n_irregular_out) {
+    if (n_str < 0 || text_len < 0 || max_segs < 0 || !n_dom_out || !n_irregular_out) return DCTD_ERR_ARG;
+    if (n_str > 0 && (!text || !str_prot || !prot_len || !dom_str || !dom_seg_off || !seg_beg || !seg_end))
+        return DCTD_ERR_ARG;
+    int32_t n_dom = 0, n_irr = 0;
+    int64_t n_seg = 0, pos = 0;
+    if (dom_seg_off) dom_seg_off[0] = 0;
+    for (int32_t i = 0; i < n_str; ++i) {
+        const int32_t p = str_prot[i];
+        if (p < 0 || p >= n_prot) return DCTD_ERR_ARG;
+        const int64_t rows_p = prot_len[p];
+        const int64_t seg0 = n_seg;
+        int64_t rows = 0;
+        bool regular = true, at_end = false;
+        // one string: "beg-end" segments separated by ',', terminated by '\n' (or the end of the text)
+        while (!at_end) {
+            int64_t v[2] = {0, 0};
+            for (int part = 0; part < 2 && regular; ++part) {
+                int digits = 0;
+                while (pos < text_len && text[pos] >= '0' && text[pos] <= '9') {
+                    if (v[part] < (1LL << 40)) v[part] = v[part] * 10 + (text[pos] - '0');
+                    ++pos;
+                    ++digits;
+                }
+                if (digits == 0) regular = false;
+                if (part == 0) {
+                    if (pos < text_len && text[pos] == '-') ++pos;
+                    else regular = false;
+                }
+            }
+            if (regular) {
+                // reference: a segment whose begin lies beyond the protein (or begin 0) takes get_doms' special paths
+                if (v[0] < 1 || v[0] > rows_p) {
+                    regular = false;
+                } else if (n_seg >= max_segs) {
+                    return DCTD_ERR_WORKSPACE;
+                } else {
+                    const int64_t lo = v[0] - 1, hi = v[1] < rows_p ? v[1] : rows_p;
+                    seg_beg[n_seg] = (int32_t)lo;
+                    seg_end[n_seg] = (int32_t)(hi > lo ? hi : lo);
+                    rows += seg_end[n_seg] - seg_beg[n_seg];
+                    ++n_seg;
+                }
+            }
+            if (regular && pos < text_len && text[pos] == ',') {
+                ++pos;
+                continue;
+            }
+            if (!(pos >= text_len || text[pos] == '\n')) regular = false;      // anything else: leave it to the caller
+            while (pos < text_len && text[pos] != '\n') ++pos;               // skip to the end of this string
+            if (pos < text_len) ++pos;
+            at_end = true;
+        }
+        if (!regular) {
+            ++n_irr;
+            n_seg = seg0;
+            continue;
+        }
+        if (rows == 0) {          // reference: an empty embedding slice -> the domain is skipped
+            n_seg = seg0;
+            continue;
+        }
+        dom_str[n_dom] = i;
+        dom_seg_off[n_dom + 1] = (int32_t)n_seg;
+        ++n_dom;
+    }
+    *n_dom_out = n_dom;
+    *n_irregular_out = n_irr;
     return DCTD_OK;
 }
 

@@ -30,6 +30,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <mutex>
 #include <new>
 #include <vector>
 
@@ -111,7 +112,6 @@ struct dctd_fp_plan {
     std::vector<Piece> pieces;
     std::vector<DomInfo> doms;
     std::vector<Item> items;
-    std::vector<int32_t> wsitems;   // 32 words per item (fp_ws_kernel.cuh), same order as items
     bool has_rider;           // some items carry their protein's global fingerprint along
     uint32_t flags;           // DCTD_FP_PLAN_* options the plan was created with
     int32_t n_counters;       // 1 (work queue) + split arrival counters
@@ -119,9 +119,12 @@ struct dctd_fp_plan {
     int64_t algo_bytes;
     // device blob layout (bytes from the workspace base)
     size_t off_pieces, off_doms, off_items, off_wsitems, off_src, off_counters, off_timing, off_table, off_partials, total;
-    void *blob;               // host copy of [pieces | doms | items], pinned when possible
+    void *blob;               // host copy of [pieces | doms | items | 32-word item records], pinned when possible
     bool blob_pinned;
-    size_t blob_bytes;
+    size_t blob_bytes;        // bytes uploaded
+    size_t blob_capacity;     // bytes allocated (blobs are recycled through a small cache, see blob_acquire)
+    mutable cudaEvent_t uploaded;   // recorded after the last upload of the blob: the blob is not recycled before it
+    mutable bool has_event;
 };
 
 namespace {
@@ -806,6 +809,58 @@ constexpr int g_variant = 0;
 constexpr int g_ws_stages = 0;
 #endif
 
+// Host blobs of the plans (pinned when a device is present) are recycled through a small cache: cudaHostAlloc /
+// mmap + page faults per plan cost more than building the plan (0.7 -> 0.3 ms for 512 proteins).  This is memory
+// management only: a blob carries no state from one plan to the next.
+struct HostBlob { void *p; size_t bytes; bool pinned; };
+std::mutex g_blob_mu;
+std::vector<HostBlob> g_blobs;
+size_t g_blob_cached = 0;
+constexpr size_t kBlobCacheBytes = 256u << 20;
+constexpr size_t kBlobCacheEntries = 16;
+
+void blob_free(const HostBlob &b) {
+    if (b.pinned) cudaFreeHost(b.p);
+    else free(b.p);
+}
+HostBlob blob_acquire(size_t bytes) {
+    {
+        std::lock_guard<std::mutex> lk(g_blob_mu);
+        int best = -1;
+        for (int i = 0; i < (int)g_blobs.size(); ++i)
+            if (g_blobs[i].bytes >= bytes && g_blobs[i].bytes <= 4 * bytes + (1u << 20) &&
+                (best < 0 || g_blobs[i].bytes < g_blobs[best].bytes)) best = i;
+        if (best >= 0) {
+            HostBlob b = g_blobs[best];
+            g_blobs.erase(g_blobs.begin() + best);
+            g_blob_cached -= b.bytes;
+            return b;
+        }
+    }
+    HostBlob b{nullptr, dctd::align_up(bytes + bytes / 4, 64u << 10), false};
+    if (cudaHostAlloc(&b.p, b.bytes, cudaHostAllocDefault) == cudaSuccess) {
+        b.pinned = true;
+    } else {
+        (void)cudaGetLastError();   // no device (CPU-only planning): plain host memory
+        b.p = malloc(b.bytes);
+    }
+    return b;
+}
+void blob_release(const HostBlob &b) {
+    std::vector<HostBlob> drop;
+    {
+        std::lock_guard<std::mutex> lk(g_blob_mu);
+        g_blobs.push_back(b);
+        g_blob_cached += b.bytes;
+        while (g_blobs.size() > kBlobCacheEntries || g_blob_cached > kBlobCacheBytes) {
+            drop.push_back(g_blobs.front());
+            g_blob_cached -= g_blobs.front().bytes;
+            g_blobs.erase(g_blobs.begin());
+        }
+    }
+    for (const HostBlob &d : drop) blob_free(d);
+}
+
 // Queue order of the items.  The persistent CTAs pull items from one atomic queue.  Longest first (LPT) balances the
 // tail, but it also makes every CTA stream long items at the start of the launch (HBM-bound, finisher warps idle) and
 // short ones at its end (finisher-bound: an item's passes 2 cost ~19 k cycles whatever its length, HBM idle).  So the
@@ -978,7 +1033,8 @@ int dctd_fp_plan_create_ex(const dctd_fp_geometry *geo, uint32_t flags, dctd_fp_
     pl->n_layers = geo->n_layers; pl->D = geo->D; pl->n = geo->n; pl->m = geo->m;
     pl->n_src = geo->n_src; pl->n_dom = geo->n_dom;
     pl->flags = flags;
-    pl->blob = nullptr; pl->blob_pinned = false; pl->blob_bytes = 0;
+    pl->blob = nullptr; pl->blob_pinned = false; pl->blob_bytes = 0; pl->blob_capacity = 0;
+    pl->has_event = false;
     pl->algo_bytes = 0;
     int rc = DCTD_OK;
     try {
@@ -1054,24 +1110,40 @@ int dctd_fp_plan_create_ex(const dctd_fp_geometry *geo, uint32_t flags, dctd_fp_
             if (rc == DCTD_OK && (dom_len[i] < geo->n || dom_len[i] > (1 << 26))) rc = DCTD_ERR_ARG;  // reference: reshape fails for L < n
         }
         std::vector<int32_t> global_of((size_t)geo->n_prot, -1);   // fused proteins: index of the global domain
-        std::vector<std::vector<std::pair<int64_t, int64_t>>> filler((size_t)geo->n_prot);
-        std::vector<std::vector<int32_t>> by_prot((size_t)geo->n_prot);
+        // domains grouped by protein and the filler ranges of the fused proteins, both as offset + flat arrays
+        std::vector<int32_t> bp_off((size_t)geo->n_prot + 1, 0), bp((size_t)geo->n_dom);
+        std::vector<int32_t> fill_off((size_t)geo->n_prot + 1, 0);
+        std::vector<std::pair<int64_t, int64_t>> fill;
         if (rc == DCTD_OK && !(flags & DCTD_FP_PLAN_NO_FUSION) && geo->n <= 4) {      // rider kernels are built for n <= 4 (2n - 2 projections)
-            for (int i = 0; i < geo->n_dom; ++i) by_prot[geo->dom_prot[i]].push_back(i);
+            for (int i = 0; i < geo->n_dom; ++i) ++bp_off[geo->dom_prot[i] + 1];
+            for (int p = 0; p < geo->n_prot; ++p) bp_off[p + 1] += bp_off[p];
+            {
+                std::vector<int32_t> cur(bp_off.begin(), bp_off.end() - 1);
+                for (int i = 0; i < geo->n_dom; ++i) bp[cur[geo->dom_prot[i]]++] = i;
+            }
+            std::vector<std::pair<int64_t, int64_t>> segs;
             for (int p = 0; p < geo->n_prot; ++p) {
+                fill_off[p + 1] = (int32_t)fill.size();
+                const int32_t *mine = bp.data() + bp_off[p];
+                const int n_mine = bp_off[p + 1] - bp_off[p];
                 int gdom = -1;
-                for (int i : by_prot[p]) {
-                    const int j = geo->dom_seg_off[i];
+                for (int t = 0; t < n_mine; ++t) {
+                    const int i = mine[t], j = geo->dom_seg_off[i];
                     if (geo->dom_seg_off[i + 1] - j == 1 && geo->seg_beg[j] == 0 && geo->seg_end[j] == plen[p]) { gdom = i; break; }
                 }
-                if (gdom < 0 || by_prot[p].size() < 2) continue;
-                std::vector<std::pair<int64_t, int64_t>> segs;
-                for (int i : by_prot[p]) {
+                if (gdom < 0 || n_mine < 2) continue;
+                segs.clear();
+                bool sorted = true;
+                for (int t = 0; t < n_mine; ++t) {
+                    const int i = mine[t];
                     if (i == gdom) continue;
                     for (int j = geo->dom_seg_off[i]; j < geo->dom_seg_off[i + 1]; ++j)
-                        if (geo->seg_end[j] > geo->seg_beg[j]) segs.emplace_back(geo->seg_beg[j], geo->seg_end[j]);
+                        if (geo->seg_end[j] > geo->seg_beg[j]) {
+                            if (!segs.empty() && geo->seg_beg[j] < segs.back().first) sorted = false;
+                            segs.emplace_back(geo->seg_beg[j], geo->seg_end[j]);
+                        }
                 }
-                std::sort(segs.begin(), segs.end());
+                if (!sorted) std::sort(segs.begin(), segs.end());
                 bool disjoint = true;
                 for (size_t t = 1; t < segs.size(); ++t)
                     if (segs[t].first < segs[t - 1].second) { disjoint = false; break; }
@@ -1079,12 +1151,15 @@ int dctd_fp_plan_create_ex(const dctd_fp_geometry *geo, uint32_t flags, dctd_fp_
                 global_of[p] = gdom;
                 int64_t pos = 0;
                 for (auto &sg : segs) {
-                    if (sg.first > pos) filler[p].emplace_back(pos, sg.first);
+                    if (sg.first > pos) fill.emplace_back(pos, sg.first);
                     pos = sg.second;
                 }
-                if (pos < plen[p]) filler[p].emplace_back(pos, plen[p]);
+                if (pos < plen[p]) fill.emplace_back(pos, plen[p]);
+                fill_off[p + 1] = (int32_t)fill.size();
             }
         }
+        pl->pieces.reserve((geo->n_dom > 0 ? (size_t)geo->dom_seg_off[geo->n_dom] : 0) + 2 * (size_t)geo->n_prot + fill.size());
+        pl->items.reserve((size_t)geo->n_layers * ((size_t)geo->n_dom + fill.size()) * 5 / 4 + 16);
 
         // ---- pieces, domains, items ----
         std::vector<int32_t> pivot_piece((size_t)geo->n_prot, -1);
@@ -1096,7 +1171,7 @@ int dctd_fp_plan_create_ex(const dctd_fp_geometry *geo, uint32_t flags, dctd_fp_
             if (!fused_global) continue;
             DomInfo di{};
             di.piece_off = (int32_t)pl->pieces.size();
-            for (auto &rg : filler[p]) add_pieces(p, rg.first, rg.second, rg.first);
+            for (int32_t t = fill_off[p]; t < fill_off[p + 1]; ++t) add_pieces(p, fill[t].first, fill[t].second, fill[t].first);
             di.n_pieces = (int32_t)pl->pieces.size() - di.piece_off;
             di.L = (int32_t)dom_len[i];
             pivot_piece[p] = (int32_t)pl->pieces.size();
@@ -1107,8 +1182,8 @@ int dctd_fp_plan_create_ex(const dctd_fp_geometry *geo, uint32_t flags, dctd_fp_
             for (int pi = 0; pi < di.n_pieces; ++pi)
                 n_fill += (pl->pieces[di.piece_off + pi].nrows + kRowsPerItem - 1) / kRowsPerItem;
             int n_ride = 0;
-            for (int o : by_prot[p])
-                if (o != i) n_ride += (int)((dom_len[o] + kRowsPerItem - 1) / kRowsPerItem);
+            for (int32_t t = bp_off[p]; t < bp_off[p + 1]; ++t)
+                if (const int o = bp[t]; o != i) n_ride += (int)((dom_len[o] + kRowsPerItem - 1) / kRowsPerItem);
             di.nsplit = n_fill + n_ride;
             di.slab0 = (int32_t)n_slabs;
             n_slabs += (int64_t)di.nsplit * geo->n_layers;
@@ -1178,19 +1253,51 @@ int dctd_fp_plan_create_ex(const dctd_fp_geometry *geo, uint32_t flags, dctd_fp_
         }
         if (rc == DCTD_OK) {
             // longest items first: the atomic work queue then behaves like LPT scheduling
-            std::stable_sort(pl->items.begin(), pl->items.end(), [](const Item &a, const Item &b) {
-                return (a.r1 - a.r0) > (b.r1 - b.r0);
-            });
+            {   // stable counting sort by length (an item has at most kRowsPerItem rows)
+                std::vector<int32_t> start((size_t)kRowsPerItem + 2, 0);
+                auto bucket = [](const Item &it) { return kRowsPerItem - std::min(std::max(it.r1 - it.r0, 0), kRowsPerItem); };
+                for (const Item &it : pl->items) ++start[bucket(it) + 1];
+                for (int l = 0; l <= kRowsPerItem; ++l) start[l + 1] += start[l];
+                std::vector<Item> sorted(pl->items.size());
+                for (const Item &it : pl->items) sorted[start[bucket(it)]++] = it;
+                pl->items.swap(sorted);
+            }
             if (!(flags & DCTD_FP_PLAN_LONGEST_FIRST)) spread_short_items(pl->items, geo->D);
             pl->n_counters = n_counters;
             pl->n_slabs = n_slabs;
+            size_t off = 0;
+            pl->off_pieces = off; off += dctd::align_up(pl->pieces.size() * sizeof(Piece), 256);
+            pl->off_doms = off;   off += dctd::align_up(pl->doms.size() * sizeof(DomInfo), 256);
+            pl->off_items = off;  off += dctd::align_up(pl->items.size() * sizeof(Item), 256);
+            pl->off_wsitems = off; off += dctd::align_up(pl->items.size() * 32 * sizeof(int32_t), 256);
+            pl->blob_bytes = off;
+            pl->off_src = off;      off += dctd::align_up((size_t)geo->n_layers * geo->n_src * sizeof(void *), 256);
+            pl->off_counters = off; off += dctd::align_up((size_t)n_counters * sizeof(int), 256);
+            pl->off_timing = off;   off += 256;
+            pl->off_table = off;    off += dctd::align_up((size_t)(4 * geo->D + 8 * geo->m) * sizeof(float), 256);
+            pl->off_partials = off; off += dctd::align_up((size_t)n_slabs * (geo->n - 1) * geo->D * sizeof(double), 256);
+            pl->total = off;
+            int32_t *records = nullptr;
+            if (pl->blob_bytes) {
+                const HostBlob hb = blob_acquire(pl->blob_bytes);
+                if (!hb.p) {
+                    rc = DCTD_ERR_NOMEM;
+                } else {
+                    char *h = (char *)hb.p;
+                    pl->blob = hb.p; pl->blob_pinned = hb.pinned; pl->blob_capacity = hb.bytes;
+                    if (!pl->pieces.empty()) memcpy(h + pl->off_pieces, pl->pieces.data(), pl->pieces.size() * sizeof(Piece));
+                    if (!pl->doms.empty()) memcpy(h + pl->off_doms, pl->doms.data(), pl->doms.size() * sizeof(DomInfo));
+                    if (!pl->items.empty()) memcpy(h + pl->off_items, pl->items.data(), pl->items.size() * sizeof(Item));
+                    records = (int32_t *)(h + pl->off_wsitems);
+                    memset(records, 0, pl->items.size() * 32 * sizeof(int32_t));
+                }
+            }
             // fat item records of the warp-specialised kernel: everything its producer / finisher warps need
-            // about an item in one 128-byte read (see the word indices in fp_ws_kernel.cuh)
-            pl->wsitems.assign(pl->items.size() * 32, 0);
-            for (size_t t = 0; t < pl->items.size(); ++t) {
+            // about an item in one 128-byte read (see the word indices in fp_ws_kernel.cuh), built in place
+            for (size_t t = 0; records && t < pl->items.size(); ++t) {
                 const Item &itm = pl->items[t];
                 const DomInfo &di = pl->doms[itm.dom];
-                int32_t *w = &pl->wsitems[t * 32];
+                int32_t *w = records + t * 32;
                 w[kWDom] = itm.dom; w[kWLayer] = itm.layer; w[kWR0] = itm.r0; w[kWR1] = itm.r1; w[kWL] = di.L;
                 int32_t fl = 0;
                 w[kWSplit] = itm.split; w[kWNsplit] = di.nsplit;
@@ -1233,36 +1340,6 @@ int dctd_fp_plan_create_ex(const dctd_fp_geometry *geo, uint32_t flags, dctd_fp_
                     fl |= kWfPivotInline;
                 w[kWFlags] = fl;
             }
-            size_t off = 0;
-            pl->off_pieces = off; off += dctd::align_up(pl->pieces.size() * sizeof(Piece), 256);
-            pl->off_doms = off;   off += dctd::align_up(pl->doms.size() * sizeof(DomInfo), 256);
-            pl->off_items = off;  off += dctd::align_up(pl->items.size() * sizeof(Item), 256);
-            pl->off_wsitems = off; off += dctd::align_up(pl->wsitems.size() * sizeof(int32_t), 256);
-            pl->blob_bytes = off;
-            pl->off_src = off;      off += dctd::align_up((size_t)geo->n_layers * geo->n_src * sizeof(void *), 256);
-            pl->off_counters = off; off += dctd::align_up((size_t)n_counters * sizeof(int), 256);
-            pl->off_timing = off;   off += 256;
-            pl->off_table = off;    off += dctd::align_up((size_t)(4 * geo->D + 8 * geo->m) * sizeof(float), 256);
-            pl->off_partials = off; off += dctd::align_up((size_t)n_slabs * (geo->n - 1) * geo->D * sizeof(double), 256);
-            pl->total = off;
-            if (pl->blob_bytes) {
-                void *h = nullptr;
-                if (cudaHostAlloc(&h, pl->blob_bytes, cudaHostAllocDefault) == cudaSuccess) {
-                    pl->blob_pinned = true;
-                } else {
-                    (void)cudaGetLastError();   // no device (CPU-only planning): plain host memory
-                    h = malloc(pl->blob_bytes);
-                    if (!h) rc = DCTD_ERR_NOMEM;
-                }
-                if (h) {
-                    memset(h, 0, pl->blob_bytes);
-                    if (!pl->pieces.empty()) memcpy((char *)h + pl->off_pieces, pl->pieces.data(), pl->pieces.size() * sizeof(Piece));
-                    if (!pl->doms.empty()) memcpy((char *)h + pl->off_doms, pl->doms.data(), pl->doms.size() * sizeof(DomInfo));
-                    if (!pl->items.empty()) memcpy((char *)h + pl->off_items, pl->items.data(), pl->items.size() * sizeof(Item));
-                    if (!pl->wsitems.empty()) memcpy((char *)h + pl->off_wsitems, pl->wsitems.data(), pl->wsitems.size() * sizeof(int32_t));
-                    pl->blob = h;
-                }
-            }
         }
     } catch (const std::bad_alloc &) {
         rc = DCTD_ERR_NOMEM;
@@ -1277,10 +1354,11 @@ int dctd_fp_plan_create_ex(const dctd_fp_geometry *geo, uint32_t flags, dctd_fp_
 
 void dctd_fp_plan_destroy(dctd_fp_plan *plan) {
     if (!plan) return;
-    if (plan->blob) {
-        if (plan->blob_pinned) cudaFreeHost(plan->blob);
-        else free(plan->blob);
+    if (plan->has_event) {
+        (void)cudaEventSynchronize(plan->uploaded);     // an upload of the blob may still be in flight
+        (void)cudaEventDestroy(plan->uploaded);
     }
+    if (plan->blob) blob_release(HostBlob{plan->blob, plan->blob_capacity, plan->blob_pinned});
     delete plan;
 }
 
@@ -1326,7 +1404,7 @@ int dctd_fp_plan_dump(const dctd_fp_plan *plan, int32_t *pieces, int64_t max_pie
 int dctd_fp_plan_dump_records(const dctd_fp_plan *plan, int32_t *records, int64_t max_items) {
     if (!plan || !records || max_items < 0) return DCTD_ERR_ARG;
     const size_t n = std::min<size_t>((size_t)max_items, plan->items.size());
-    if (n) memcpy(records, plan->wsitems.data(), n * 32 * sizeof(int32_t));
+    if (n) memcpy(records, (const char *)plan->blob + plan->off_wsitems, n * 32 * sizeof(int32_t));
     return DCTD_OK;
 }
 
@@ -1358,6 +1436,11 @@ int dctd_fp_execute(const dctd_fp_plan *plan, const void *const *h_src_ptrs, int
 
     if (!(flags & DCTD_FP_TABLES_RESIDENT)) {
         DCTD_CUDA_TRY(cudaMemcpyAsync(ws, plan->blob, plan->blob_bytes, cudaMemcpyHostToDevice, stream));
+        if (!plan->has_event) {
+            DCTD_CUDA_TRY(cudaEventCreateWithFlags(&plan->uploaded, cudaEventDisableTiming));
+            plan->has_event = true;
+        }
+        DCTD_CUDA_TRY(cudaEventRecord(plan->uploaded, stream));
         fp_table_kernel<<<8, 256, 0, stream>>>((float *)(ws + plan->off_table), plan->D, prm.lay.table_len);
         DCTD_LAUNCH_CHECK();
     }

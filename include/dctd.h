@@ -11,7 +11,8 @@
  *     named h_* / "host" are host pointers; the caller owns every buffer including workspaces;
  *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); all device work
  *     is stream-ordered on it and the functions do not synchronise unless stated;
- *   - the library keeps no global mutable state besides a thread-local "last CUDA error" and launch counter: options
+ *   - the library keeps no global mutable state besides a thread-local "last CUDA error" and launch counter and an
+ *     internal cache of host staging buffers (memory management only): options
  *     are per plan / per call (flags).  The A/B switches used while tuning (dctd_fp_set_variant, dctd_l1_set_mode) exist
  *     only in the separate tuning build (make -C dctdomain_b200/csrc tuning), not in libdctd.so.
  */
@@ -96,6 +97,20 @@ typedef struct dctd_fp_geometry {
     const int32_t *seg_beg;     /* host [n_seg] 0-based first row */
     const int32_t *seg_end;     /* host [n_seg] exclusive end row (already clipped to the protein) */
 } dctd_fp_geometry;
+
+/* RecCut domain strings of a whole batch -> the segment arrays of dctd_fp_geometry, with get_doms' rules
+ * (src/fingerprint.py:160-171: 1-based inclusive "beg-end" segments separated by ',', rows in listed order, an end beyond
+ * the protein is clipped).  text: the n_str strings, each terminated by '\n'; str_prot[i]: protein of string i;
+ * prot_len[p]: rows of protein p.  Strings with no rows are dropped (the reference skips them); domain j of the output
+ * comes from string dom_str[j] and owns segments dom_seg_off[j] .. dom_seg_off[j+1]-1 (0-based begin, exclusive end).
+ * Strings that need the reference's special paths - a begin beyond the protein (the segment is dropped and the next one
+ * passed over, fingerprint.py:163-165), a begin < 1, anything that is not digits - are counted in *n_irregular and left
+ * out: the caller handles those with its mirror of the reference code (dctdomain_b200.fingerprint.parse_domain).
+ * max_segs: capacity of seg_beg / seg_end (number of ',' in text + n_str is enough).  Host only. */
+int dctd_parse_domains(const char *text, int64_t text_len, int32_t n_str, const int32_t *str_prot,
+                       const int32_t *prot_len, int32_t n_prot, int32_t *dom_str, int32_t *dom_seg_off,
+                       int32_t *seg_beg, int32_t *seg_end, int64_t max_segs, int32_t *n_dom,
+                       int32_t *n_irregular);
 
 /* Builds the work decomposition (pieces; items of at most 512 rows in queue order: long items longest first with the
  * short ones spread evenly between them).  Host only. */

@@ -322,3 +322,58 @@ def test_queue_order_spreads_short_items_and_keeps_every_item(lib):
     frac = cum_long[pos] / total
     want = (np.arange(len(pos)) + 0.5) / len(pos)
     assert np.abs(frac - want).max() < 0.01
+
+
+def test_batch_domain_parser_matches_the_line_by_line_mirror(lib):
+    """dctd_parse_domains (one C call per batch) against parse_domain, the mirror of get_doms' bound handling
+    (src/fingerprint.py:160-171): clipped ends, empty strings skipped, and - through the fallback - the dropped-segment
+    quirk, begin 0, anything malformed."""
+    from dctdomain_b200.fingerprint import parse_domain, parse_domains_batch
+    rs = np.random.RandomState(3)
+
+    def mirror(dom_lists, plen):
+        dp, off, sb, se, names = [], [0], [], [], []
+        for pi, doms in enumerate(dom_lists):
+            for dom in doms:
+                segs, kept = parse_domain(dom, plen[pi])
+                if sum(e - b for b, e in segs) == 0:
+                    continue
+                names.append(kept); dp.append(pi)
+                for b, e in segs:
+                    sb.append(b); se.append(e)
+                off.append(len(sb))
+        return dp, off, sb, se, names
+
+    def check(dom_lists, plen):
+        got = parse_domains_batch(dom_lists, plen)
+        want = mirror(dom_lists, plen)
+        for g, w in zip(got[:4], want[:4]):
+            assert np.asarray(g).tolist() == list(w)
+        assert list(got[4]) == want[4]
+
+    for trial in range(30):
+        n_prot = rs.randint(1, 40)
+        plen = rs.randint(5, 400, size=n_prot).tolist()
+        dom_lists = []
+        for L in plen:
+            doms = []
+            for _ in range(rs.randint(0, 5)):
+                segs = []
+                for _ in range(rs.randint(1, 4)):
+                    a = rs.randint(1, L + 1)
+                    b = rs.randint(1, L + 30)            # ends beyond the protein are clipped, ends below the begin are empty
+                    segs.append(f'{a}-{b}')
+                doms.append(','.join(segs))
+            dom_lists.append(doms)
+        check(dom_lists, plen)                           # regular strings only: the C path
+        if trial % 3 == 0:                               # irregular strings: the fallback must give the same
+            p = rs.randint(n_prot)
+            L = plen[p]
+            dom_lists[p] = dom_lists[p] + [f'{L + 5}-{L + 9},3-4,1-2', f'0-{min(L, 7)}', f'1-{L}']
+            check(dom_lists, plen)
+    check([[], ['1-5']], [10, 10])
+    check([['7-3'], ['2-2']], [10, 10])                  # an empty and a one-row domain
+    with pytest.raises(ValueError):
+        parse_domains_batch([['1-5-7']], [10])           # the reference's split('-') fails the same way
+    with pytest.raises(ValueError):
+        parse_domains_batch([['a-5']], [10])
