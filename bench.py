@@ -390,6 +390,11 @@ def run_ours(args):
         else:
             search = search_1m
 
+    # ---- dct-sim --db / all-vs-all: protein-level scores for all pairs of two sets ----
+    dctsim = None
+    if not args.no_search and not args.no_dctsim and rank == 0:
+        dctsim = run_dctsim(torch, dev, L, cores)
+
     # ---- CPU baseline (rank 0, N = 1 only) ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -413,7 +418,7 @@ def run_ours(args):
             'config': primary_config(B, len(pool), world),
             'clocks': clocks, 'e2e': e2e, 'e2e_device': e2e_device, 'gpu_launches': launches, 'roofline': roofline, 'cpu_baseline': cpu,
             'protein_batch': fused, 'long_sequences': longseq, 'search': search, 'search_1m': search_1m,
-            'search_allvsall': allvsall, 'search_stream': stream,
+            'search_allvsall': allvsall, 'search_stream': stream, 'dct_sim_all_pairs': dctsim,
             # part (ii) of the metric, for the strong-scaling curve (the primary line above is collective-free by nature)
             'search_scaling_input': None if search is None else {
                 'metric': search['metric'], 'value': search['value'], 'unit': 'pairs/s', 'scaling': 'strong',
@@ -847,6 +852,70 @@ def run_search_stream(args, sh, dev, rank, world, dist, torch, barrier, max_over
                          'kernel': 'l1 streaming kernel (csrc/l1topk.cu), every shard streamed once per call'}}
 
 
+def run_dctsim(torch, dev, L, cores, n_prot=10_000):
+    """`dct-sim.py --db` at scale (src/dct-sim.py:126-156): n_prot query proteins against n_prot database proteins, 2-7
+    fingerprints each (RecCut domains + the global one); per protein pair the minimum over all fingerprint pairs and the
+    last-vs-last distance.  Device time of dctd_l1_protein_scores (both sets resident), the whole call from host arrays,
+    and a numpy check of a sample of protein pairs."""
+    from dctdomain_b200 import dct_sim
+    rs = np.random.RandomState(11)
+    sets = []
+    for sd in (1, 2):
+        counts = rs.randint(2, 8, size=n_prot)
+        off = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+        sets.append((synth_rows(torch, dev, int(off[-1]), 500 + sd), off))
+    (qf, qoff), (df, doff) = sets
+    n_qf, n_df = int(qoff[-1]), int(doff[-1])
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    packed = torch.empty(int(L.dctd_l1_packed_bytes(n_df, 480)), dtype=torch.uint8, device=dev)
+    L.dctd_l1_pack(df.data_ptr(), n_df, 480, 0, packed.data_ptr(), stream)
+    ws = torch.empty(int(L.dctd_l1_protein_scores_workspace_bytes(n_qf, n_prot, n_df, n_prot, 480)), dtype=torch.uint8, device=dev)
+    mn = torch.empty((n_prot, n_prot), dtype=torch.int32, device=dev)
+    last = torch.empty_like(mn)
+
+    def call():
+        rc = L.dctd_l1_protein_scores(qf.data_ptr(), qoff.ctypes.data, n_prot, packed.data_ptr(), doff.ctypes.data, n_prot, 480,
+                                      mn.data_ptr(), last.data_ptr(), ws.data_ptr(), ws.numel(), stream)
+        assert rc == 0, rc
+
+    call()
+    torch.cuda.synchronize()
+    L.dctd_launch_count(1)
+    steps = 3
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        call()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    launches = int(L.dctd_launch_count(0)) // steps
+    qh, dh = qf.cpu().numpy(), df.cpu().numpy()
+    t0 = time.perf_counter()
+    hm, hl = dct_sim.protein_scores(qh, qoff, dh, doff)
+    e2e_s = time.perf_counter() - t0
+    bad = 0
+    sel = rs.randint(0, n_prot, size=(64, 2))
+    for a, b in sel:
+        blk = np.abs(qh[qoff[a]:qoff[a + 1], None, :].astype(np.int32) - dh[None, doff[b]:doff[b + 1], :].astype(np.int32)).sum(axis=2)
+        bad += int(hm[a, b] != blk.min() or hl[a, b] != blk[-1, -1])
+    same = bool(np.array_equal(mn.cpu().numpy(), hm) and np.array_equal(last.cpu().numpy(), hl))
+    fp_pairs = float(n_qf) * n_df
+    sad = fp_pairs * 120 / (ms * 1e-3)
+    return {'metric': 'protein pairs/s (dct-sim --db: min over fingerprint pairs + last-vs-last)', 'value': float(n_prot) * n_prot / ms * 1e3,
+            'unit': 'protein pairs/s', 'ms_per_step': ms, 'steps': steps, 'gpu_launches': launches, 'dtype': 'u8',
+            'fingerprint_pairs_per_s': fp_pairs / ms * 1e3,
+            'e2e': {'value': float(n_prot) * n_prot / e2e_s, 'unit': 'protein pairs/s', 'seconds': e2e_s,
+                    'h2d_bytes_per_step': (n_qf + n_df) * 480, 'd2h_bytes_per_step': 2 * n_prot * n_prot * 4,
+                    'api': 'dctdomain_b200.dct_sim.protein_scores(host arrays) -> int64 [n_q, n_db] x 2 (pack + kernel + D2H + widening)'},
+            'parity': {'checked': 64, 'mismatches': bad, 'oracle': 'numpy |a - b|.sum over every fingerprint pair of 64 random protein pairs',
+                       'device_api_equals_host_api': same},
+            'config': {'workload': f'{n_prot} x {n_prot} proteins, 2-7 int8[480] fingerprints each ({n_qf} x {n_df} fingerprint pairs)'},
+            'roofline': {'bound': 'integer pipe (VABSDIFF4.U8.ACC, 120 per fingerprint pair)', 'achieved': sad, 'peak': SAD4_PEAK_PER_GPU,
+                         'unit': 'SAD4 lane-ops/s', 'frac': sad / SAD4_PEAK_PER_GPU,
+                         'kernel': 'l1_protein_kernel<16,8,2,4,30> + l1_protein_reduce_kernel (csrc/l1_protein.cuh)'}}
+
+
 def cpu_search_rate(cores):
     """pairs/s of the faiss-style CPU restatement (oracle/l1_flat.c: float32 database, OpenMP over queries) on a
     bounded sample of the configs[3] workload."""
@@ -886,6 +955,7 @@ def main():
     ap.add_argument('--no-cfg4', action='store_true')
     ap.add_argument('--no-allvsall', action='store_true')
     ap.add_argument('--no-search', action='store_true')
+    ap.add_argument('--no-dctsim', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--no-fused', action='store_true')
     args = ap.parse_args()

@@ -26,6 +26,8 @@
 
 #include <algorithm>
 #include <mutex>
+#include <new>
+#include <vector>
 
 #include "dctd_internal.cuh"
 #include "dctd_tma.cuh"
@@ -852,6 +854,8 @@ __global__ void __launch_bounds__(128) l1_merge_kernel(const MergeParams p) {
     }
 }
 
+#include "l1_protein.cuh"
+
 // ------------------------------------------------------------------------------------------
 // pairwise scorer (dct-sim.py:12-50): one warp per protein pair
 // ------------------------------------------------------------------------------------------
@@ -1605,6 +1609,130 @@ int dctd_l1_pair_scores(const int8_t *d_fps, int32_t d, const int64_t *d_off, co
         pair_scores_kernel<false><<<grid, warps * 32, 0, (cudaStream_t)stream>>>(
             d_fps, d, (const long long *)d_off, d_pair_a, d_pair_b, n_pairs, d_min_dist, d_last_dist);
     DCTD_LAUNCH_CHECK();
+    return DCTD_OK;
+}
+
+/* protein-level scores for all pairs of two sets: see dctd.h */
+size_t dctd_l1_protein_scores_workspace_bytes(int64_t n_qf, int64_t n_qprot, int64_t n_dbf, int64_t n_dbprot, int32_t d) {
+    if (n_qf < 0 || n_qprot < 0 || n_dbf < 0 || n_dbprot < 0 || d < 1) return 0;
+    const size_t ld = (size_t)((n_dbf + 31) / 32) * 32;
+    const size_t rows_all = (size_t)n_qprot * 2 + (size_t)(n_qf + 7) / 8;       // segments + last rows, upper bound
+    const size_t rows_min = 128 + 128 + 16;                                     // one tile of single-fingerprint proteins
+    const size_t rows = std::max(rows_min, std::min(rows_all, ((size_t)1 << 30) / std::max<size_t>(1, ld * 4)));
+    size_t off = 0;
+    off += dctd::align_up(rows * ld * 4, 256);
+    off += dctd::align_up(((size_t)(n_qf + 7) / 8 + 64) * sizeof(int4), 256);   // slices
+    off += 2 * dctd::align_up(((size_t)n_qprot + 1) * sizeof(int), 256);        // segment offsets, last rows
+    off += dctd::align_up(((size_t)n_dbprot + 1) * sizeof(long long), 256);     // database offsets
+    return off + 256;
+}
+
+int dctd_l1_protein_scores(const int8_t *d_qf, const int64_t *h_qoff, int64_t n_qprot, const void *d_db_packed,
+                           const int64_t *h_doff, int64_t n_dbprot, int32_t d, int32_t *d_min_dist, int32_t *d_last_dist,
+                           void *d_workspace, size_t workspace_bytes, void *stream_) {
+    if (n_qprot < 0 || n_dbprot < 0 || d < 1) return DCTD_ERR_ARG;
+    if (n_qprot == 0 || n_dbprot == 0) return DCTD_OK;
+    if (!h_qoff || !h_doff || !d_min_dist || !d_last_dist || !d_workspace) return DCTD_ERR_ARG;
+    const int64_t n_qf = h_qoff[n_qprot], n_dbf = h_doff[n_dbprot];
+    if (h_qoff[0] != 0 || h_doff[0] != 0 || n_qf < 0 || n_dbf < 0) return DCTD_ERR_ARG;
+    for (int64_t a = 0; a < n_qprot; ++a) if (h_qoff[a + 1] < h_qoff[a]) return DCTD_ERR_ARG;
+    for (int64_t b = 0; b < n_dbprot; ++b) if (h_doff[b + 1] < h_doff[b]) return DCTD_ERR_ARG;
+    if ((n_qf > 0 && !d_qf) || (n_dbf > 0 && !d_db_packed)) return DCTD_ERR_ARG;
+    if (((uintptr_t)d_workspace & 255) != 0) return DCTD_ERR_ARG;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    DevInfo di;
+    dev_info(&di);
+    constexpr int NW = 16, TQ = 8, QT = NW * TQ;
+    const int dpad = chunks_of(d) * 16;
+    const size_t smem = 128 + (size_t)QT * dpad + (size_t)kStagesMax * kTDmax * 32 * dpad + 64;
+    if (smem > di.smem) return DCTD_ERR_UNSUPPORTED;
+    const long long n_groups = (n_dbf + 31) / 32, ld = n_groups * 32;
+    // workspace layout (the matrix region takes what is left after the tables)
+    char *ws = (char *)d_workspace;
+    size_t tables = 0;
+    auto take = [&](size_t bytes) { const size_t o = tables; tables += dctd::align_up(bytes, 256); return o; };
+    const size_t off_slices = take(((size_t)(n_qf + 7) / 8 + 64) * sizeof(int4));
+    const size_t off_seg = take(((size_t)n_qprot + 1) * sizeof(int));
+    const size_t off_last = take(((size_t)n_qprot + 1) * sizeof(int));
+    const size_t off_doff = take(((size_t)n_dbprot + 1) * sizeof(long long));
+    if (workspace_bytes < tables + 256) return DCTD_ERR_WORKSPACE;
+    const size_t mat_bytes = (workspace_bytes - tables) / 256 * 256;
+    unsigned int *mat = (unsigned int *)(ws + tables);
+    const long long rows_cap = ld > 0 ? (long long)(mat_bytes / ((size_t)ld * 4)) : (1LL << 40);
+    DCTD_CUDA_TRY(cudaMemcpyAsync(ws + off_doff, h_doff, ((size_t)n_dbprot + 1) * sizeof(long long), cudaMemcpyHostToDevice, stream));
+    std::vector<int4> slices;
+    std::vector<int> seg_off, last_row;
+    try {
+        int64_t a0 = 0;
+        while (a0 < n_qprot) {
+            // ---- the next chunk of query proteins: as many as the matrix region, the grid limits and 2^31 slots allow ----
+            slices.clear(); seg_off.assign(1, 0); last_row.clear();
+            const int64_t f0 = h_qoff[a0];
+            int64_t a1 = a0;
+            long long n_seg = 0, n_last = 0;
+            while (a1 < n_qprot && a1 - a0 < 65535) {
+                const int64_t s = h_qoff[a1] - f0, e = h_qoff[a1 + 1] - f0;        // slots of this protein
+                const long long segs = e > s ? (e - 1) / TQ - s / TQ + 1 : 0;
+                if ((n_seg + segs) + (n_last + (e > s ? 1 : 0)) > rows_cap || (e + QT - 1) / QT > 65535) break;
+                n_seg += segs;
+                seg_off.push_back((int)n_seg);
+                last_row.push_back(e > s ? (int)n_last : -1);
+                n_last += e > s ? 1 : 0;
+                ++a1;
+            }
+            if (a1 == a0) return DCTD_ERR_WORKSPACE;         // not even one protein fits
+            const int64_t nf = h_qoff[a1] - f0;
+            const long long n_tiles_q = (nf + QT - 1) / QT;
+            if (nf > 0 && n_dbf > 0) {
+                // slice table: segment / last masks per TQ slots
+                slices.assign((size_t)n_tiles_q * NW, make_int4(0, 0, 0, 0));
+                long long seg = 0, lastc = 0;
+                int64_t prot = a0;
+                while (prot < a1 && h_qoff[prot + 1] - f0 == 0) ++prot;                  // leading empty proteins
+                for (int64_t sl = 0; sl * TQ < nf; ++sl) {
+                    unsigned int segend = 0, lastm = 0;
+                    slices[(size_t)sl].x = (int)seg;
+                    slices[(size_t)sl].y = (int)lastc;
+                    for (int a = 0; a < TQ; ++a) {
+                        const int64_t slot = sl * TQ + a;
+                        if (slot >= nf) break;
+                        while (h_qoff[prot + 1] - f0 <= slot) ++prot;                    // protein of this slot (skips empty ones)
+                        const bool is_last = slot == h_qoff[prot + 1] - f0 - 1;
+                        if (is_last) { lastm |= 1u << a; ++lastc; }
+                        if (is_last || a == TQ - 1 || slot == nf - 1) { segend |= 1u << a; ++seg; }
+                    }
+                    slices[(size_t)sl].z = (int)(segend | (lastm << 8));
+                }
+                if (seg != n_seg || lastc != n_last) return DCTD_ERR_ARG;                // (cannot happen)
+                DCTD_CUDA_TRY(cudaMemcpyAsync(ws + off_slices, slices.data(), slices.size() * sizeof(int4), cudaMemcpyHostToDevice, stream));
+                ProtParams pp{};
+                pp.sp.q = d_qf + f0 * d; pp.sp.nq = nf; pp.sp.packed = (const uint4 *)d_db_packed; pp.sp.n = n_dbf;
+                pp.sp.d = d; pp.sp.k = 1; pp.sp.n_groups = n_groups; pp.sp.gstride = 1; pp.sp.skip = 0;
+                long long splits = 1;
+                pick_splits(di.sms, n_groups, kTDmax, n_tiles_q, 2, &splits, &pp.sp.groups_per_split);
+                pp.slices = (const int4 *)(ws + off_slices);
+                pp.mseg = mat;
+                pp.mlast = mat + (size_t)n_seg * ld;
+                pp.ld = ld;
+                auto fn = d == 480 ? l1_protein_kernel<NW, TQ, kTDmax, kStagesMax, 30> : l1_protein_kernel<NW, TQ, kTDmax, kStagesMax, 0>;
+                DCTD_CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                fn<<<dim3((unsigned)splits, (unsigned)n_tiles_q), (NW + 1) * 32, smem, stream>>>(pp);
+                DCTD_LAUNCH_CHECK();
+            }
+            DCTD_CUDA_TRY(cudaMemcpyAsync(ws + off_seg, seg_off.data(), seg_off.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
+            // phase 2 (also fills INT32_MAX for proteins without fingerprints)
+            // mlast rows follow protein order among the non-empty proteins: the kernel addresses row a of mlast, so
+            // empty proteins are given no row by compacting through last_row
+            DCTD_CUDA_TRY(cudaMemcpyAsync(ws + off_last, last_row.data(), last_row.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
+            l1_protein_reduce_kernel<<<dim3((unsigned)((n_dbprot + 255) / 256), (unsigned)(a1 - a0)), 256, 0, stream>>>(
+                mat, mat + (size_t)n_seg * ld, ld, (const int *)(ws + off_seg), (const int *)(ws + off_last),
+                (const long long *)(ws + off_doff), n_dbprot, d_min_dist + a0 * n_dbprot, d_last_dist + a0 * n_dbprot, n_dbprot);
+            DCTD_LAUNCH_CHECK();
+            a0 = a1;
+        }
+    } catch (const std::bad_alloc &) {
+        return DCTD_ERR_NOMEM;
+    }
     return DCTD_OK;
 }
 

@@ -1,5 +1,6 @@
 """Drop-in for reference ``src/dct-sim.py``: same functions, flags and output text; the L1
-distances come from the GPU (dctd_l1_pair_scores), the float64 similarity formula
+distances come from the GPU - listed pairs through dctd_l1_pair_scores, the all-pairs loops of ``--db`` and all-vs-all
+through dctd_l1_protein_scores (the tiled SAD kernel of the search path) - the float64 similarity formula
 ``1 - min(d / 17000, 1)`` (dct-sim.py:23-26) is applied on the host exactly as the reference does.
 
     python -m dctdomain_b200.dct_sim --dct x-dct.npz --pair x.pair --output x-dctsim.txt
@@ -8,7 +9,6 @@ from __future__ import annotations
 
 import argparse
 import time
-from operator import itemgetter
 
 import numpy as np
 import torch
@@ -20,11 +20,7 @@ from .fingerprint import _device
 def _pair_dists(fps: np.ndarray, off: np.ndarray, pa: np.ndarray, pb: np.ndarray):
     """(min over fingerprint pairs, last-vs-last) int L1 distances for protein pairs (pa[i], pb[i])."""
     dev = _device()
-    fps = np.ascontiguousarray(fps)
-    if fps.dtype != np.int8:
-        if fps.size and (fps.min() < -128 or fps.max() > 127 or not np.array_equal(np.rint(fps), fps)):
-            raise ValueError('fingerprints must be int8 valued')
-        fps = fps.astype(np.int8)
+    fps = _as_int8(fps)
     n = len(pa)
     mn = torch.empty(n, dtype=torch.int32, device=dev)
     last = torch.empty(n, dtype=torch.int32, device=dev)
@@ -38,6 +34,51 @@ def _pair_dists(fps: np.ndarray, off: np.ndarray, pa: np.ndarray, pb: np.ndarray
                                                 d_b.data_ptr(), n, mn.data_ptr(), last.data_ptr(),
                                                 torch.cuda.current_stream(dev).cuda_stream)
         _lib.check(rc, 'dctd_l1_pair_scores')
+    return mn.cpu().numpy().astype(np.int64), last.cpu().numpy().astype(np.int64)
+
+
+def _as_int8(fps: np.ndarray) -> np.ndarray:
+    fps = np.ascontiguousarray(fps)
+    if fps.dtype != np.int8:
+        if fps.size and (fps.min() < -128 or fps.max() > 127 or not np.array_equal(np.rint(fps), fps)):
+            raise ValueError('fingerprints must be int8 valued')
+        fps = fps.astype(np.int8)
+    return fps
+
+
+def protein_scores(q_fps, q_off, db_fps, db_off, workspace_bytes: int = None):
+    """(min over fingerprint pairs, last-vs-last) int L1 distances for ALL pairs of two protein sets: int64 arrays
+    [n_q, n_db] (dctd_l1_protein_scores: the tiled SAD kernel of the search path + a per-pair reduction on the device).
+    ``q_fps`` / ``db_fps``: int8-valued [n, d] arrays, or CUDA int8 tensors; protein i owns rows off[i] .. off[i+1]-1."""
+    dev = _device()
+    L = _lib.lib()
+    q_off = np.ascontiguousarray(q_off, dtype=np.int64)
+    db_off = np.ascontiguousarray(db_off, dtype=np.int64)
+    nq, nd = len(q_off) - 1, len(db_off) - 1
+    d_q = q_fps if isinstance(q_fps, torch.Tensor) else torch.from_numpy(_as_int8(q_fps)).to(dev)
+    d_db = db_fps if isinstance(db_fps, torch.Tensor) else torch.from_numpy(_as_int8(db_fps)).to(dev)
+    d = int(d_q.shape[1]) if d_q.dim() == 2 and d_q.shape[0] else int(d_db.shape[1])
+    mn = torch.empty((nq, nd), dtype=torch.int32, device=dev)
+    last = torch.empty((nq, nd), dtype=torch.int32, device=dev)
+    if nq and nd:
+        n_dbf = int(d_db.shape[0])
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            packed = torch.empty(max(int(L.dctd_l1_packed_bytes(n_dbf, d)), 16), dtype=torch.uint8, device=dev)
+            if n_dbf:
+                _lib.check(L.dctd_l1_pack(d_db.contiguous().data_ptr(), n_dbf, d, 0, packed.data_ptr(), stream), 'dctd_l1_pack')
+            need = workspace_bytes or int(L.dctd_l1_protein_scores_workspace_bytes(int(d_q.shape[0]), nq, n_dbf, nd, d))
+            ws = torch.empty(need, dtype=torch.uint8, device=dev)
+            rc = L.dctd_l1_protein_scores(d_q.contiguous().data_ptr(), q_off.ctypes.data, nq, packed.data_ptr(),
+                                          db_off.ctypes.data, nd, d, mn.data_ptr(), last.data_ptr(), ws.data_ptr(),
+                                          ws.numel(), stream)
+        if rc == _lib.ERR_UNSUPPORTED:        # vectors too wide for the tiled kernel: one warp per protein pair
+            cat = torch.cat([d_q, d_db]).cpu().numpy()
+            off = np.concatenate([q_off, db_off[1:] + q_off[-1]])
+            a, b = np.divmod(np.arange(nq * nd, dtype=np.int64), nd)
+            m1, l1 = _pair_dists(cat, off, a.astype(np.int32), (b + nq).astype(np.int32))
+            return m1.reshape(nq, nd), l1.reshape(nq, nd)
+        _lib.check(rc, 'dctd_l1_protein_scores')
     return mn.cpu().numpy().astype(np.int64), last.cpu().numpy().astype(np.int64)
 
 
@@ -139,21 +180,20 @@ def db_search(npzfile: str, dbfile: str, top: int, threshold: float, output: str
     dct, seqid = load_dct(npzfile, asmap=False)
     db_dct, db_seqid = load_dct(dbfile, asmap=False)
     nq, nd = len(seqid), len(db_seqid)
-    cat, off = _blocks(list(dct) + list(db_dct))
-    qa = np.repeat(np.arange(nq, dtype=np.int32), nd)
-    qb = np.tile(np.arange(nd, dtype=np.int32) + nq, nq)
-    mn, last = _pair_dists(cat, off, qa, qb)
+    qcat, qoff = _blocks(list(dct))
+    dcat, doff = _blocks(list(db_dct))
+    mn, last = protein_scores(qcat, qoff, dcat, doff)            # all pairs: one tiled pass on the device
+    # the reference sorts every query's hits by the global similarity, descending and stable (sorted(..., reverse=True)
+    # keeps the database order among equal keys), and prints until rank >= top and s < threshold
+    s_all = 1.0 - np.minimum(last / 17000, 1.0)                   # float64, the values _sim() produces
+    order = np.argsort(-s_all, axis=1, kind='stable')
     for i in range(nq):
-        results = []
-        for q in range(nd):
-            maxs, s = _maxs_s(mn[i * nd + q], last[i * nd + q])
-            results.append([db_seqid[q], maxs, s])
-        results_sorted = sorted(results, key=itemgetter(2), reverse=True)
-        for q in range(nd):
-            if (q >= top) and (results_sorted[q][2] < threshold):
+        for rank in range(nd):
+            q = int(order[i, rank])
+            if (rank >= top) and (s_all[i, q] < threshold):
                 break
-            hit = results_sorted[q]
-            _emit(f"{seqid[i]} {hit[0]} {hit[1]} {hit[2]}", output)
+            maxs, s = _maxs_s(mn[i, q], last[i, q])               # exactly the reference's scalar arithmetic and types
+            _emit(f"{seqid[i]} {db_seqid[q]} {maxs} {s}", output)
 
 
 def all_sim(npzfile: str, output: str):
@@ -161,11 +201,11 @@ def all_sim(npzfile: str, output: str):
     dct, seqid = load_dct(npzfile, asmap=False)
     n = len(seqid)
     cat, off = _blocks(list(dct))
-    ia, ib = np.triu_indices(n, k=1)
-    mn, last = _pair_dists(cat, off, ia.astype(np.int32), ib.astype(np.int32))
-    for i, j, a, b in zip(ia, ib, mn, last):
-        maxs, s = _maxs_s(a, b)
-        _emit(f"{seqid[i]} {seqid[j]} {maxs:.3f} {s:.3f}", output)
+    mn, last = protein_scores(cat, off, cat, off)                 # the set against itself; the upper triangle is printed
+    for i in range(n - 1):
+        for j in range(i + 1, n):
+            maxs, s = _maxs_s(mn[i, j], last[i, j])
+            _emit(f"{seqid[i]} {seqid[j]} {maxs:.3f} {s:.3f}", output)
 
 
 def main(argv=None):

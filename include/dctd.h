@@ -223,6 +223,21 @@ int dctd_l1_pair_scores(const int8_t *d_fps, int32_t d, const int64_t *d_off, co
                         const int32_t *d_pair_b, int64_t n_pairs, int32_t *d_min_dist,
                         int32_t *d_last_dist, void *stream);
 
+/* The same two scores for ALL pairs of two protein sets - dct-sim.py's db_search / all_sim loops (src/dct-sim.py:126-176) -
+ * at the rate of the search kernels: every fingerprint pair is scored once by the TMA-staged SAD tile loop, minima are
+ * taken per protein pair on the device, no per-pair index arrays.
+ *   d_qf        device int8 [h_qoff[n_qprot], d] row-major: fingerprints of the query proteins, protein a owns rows
+ *               h_qoff[a] .. h_qoff[a+1]-1 (HOST offsets, h_qoff[0] = 0)
+ *   d_db_packed the other set's fingerprints in the packed layout (dctd_l1_pack), protein b owns h_doff[b] .. h_doff[b+1]-1
+ *   d_min_dist, d_last_dist   device int32 [n_qprot, n_dbprot]; INT32_MAX where a protein has no fingerprints
+ * The query proteins are processed in as many chunks as the workspace requires (dctd_l1_protein_scores_workspace_bytes
+ * returns a size that keeps the intermediate matrices at <= 1 GB; anything from one tile of queries upwards works).
+ * DCTD_ERR_UNSUPPORTED for vectors too wide for the shared-memory tiles (d > ~1000): use dctd_l1_pair_scores. */
+size_t dctd_l1_protein_scores_workspace_bytes(int64_t n_qf, int64_t n_qprot, int64_t n_dbf, int64_t n_dbprot, int32_t d);
+int dctd_l1_protein_scores(const int8_t *d_qf, const int64_t *h_qoff, int64_t n_qprot, const void *d_db_packed,
+                           const int64_t *h_doff, int64_t n_dbprot, int32_t d, int32_t *d_min_dist,
+                           int32_t *d_last_dist, void *d_workspace, size_t workspace_bytes, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

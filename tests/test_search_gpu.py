@@ -208,8 +208,51 @@ def test_dct_sim_db_and_all(tmp_path, capsys):
     assert open(out).read().splitlines() == want
     out = str(tmp_path / 'db.txt')
     dct_sim.main(['--dct', npz, '--db', npz, '--top', '3', '--threshold', '0.3', '--output', out])
-    got = open(out).read().splitlines()
-    assert got[0].startswith('#') and got[1].split()[0] == got[1].split()[1] and got[1].split()[3] == '1.0'
+    # the whole output against the UNMODIFIED reference's (tests/golden/make_dctsim_golden.py ran src/dct-sim.py)
+    assert open(out).read() == open(os.path.join(G, 'example-dbsearch.txt')).read()
+    out = str(tmp_path / 'db2.txt')
+    dct_sim.main(['--dct', os.path.join(G, 'G6PD-dct.npz'), '--db', npz, '--output', out])      # default --top / --threshold
+    assert open(out).read() == open(os.path.join(G, 'example-dbsearch-g6pd.txt')).read()
+    assert open(str(tmp_path / 'all.txt')).read() == open(os.path.join(G, 'example-allsim.txt')).read()
+
+
+@pytest.mark.parametrize('d', [480, 100, 16])
+def test_protein_scores_all_pairs_vs_brute_force(d):
+    """dctd_l1_protein_scores (tiled SAD kernel + per-pair reduction) against numpy over every fingerprint pair: proteins
+    with 0, 1 and more than 8 fingerprints (a warp slice holds 8), query sets that do not fill a tile, a workspace small
+    enough to force several chunks of query proteins; and against the one-warp-per-pair scorer."""
+    from dctdomain_b200 import dct_sim
+    rs = np.random.RandomState(d)
+
+    def make(n_prot, hi):
+        counts = rs.randint(0, hi, size=n_prot)
+        counts[rs.randint(n_prot)] = 19
+        counts[0] = 1
+        off = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+        fps = rs.randint(-128, 128, size=(int(off[-1]), d)).astype(np.int8)
+        return fps, off
+
+    for (nq, nd, ws) in ((1, 1, None), (300, 150, None), (300, 150, 1 << 20), (37, 61, None)):
+        qf, qoff = make(nq, 7)
+        df, doff = make(nd, 9)
+        dist = np.abs(qf[:, None, :].astype(np.int32) - df[None, :, :].astype(np.int32)).sum(axis=2)      # [NQ_f, ND_f]
+        big = np.iinfo(np.int32).max
+        want_min = np.full((nq, nd), big, dtype=np.int64)
+        want_last = np.full((nq, nd), big, dtype=np.int64)
+        for a in range(nq):
+            for b in range(nd):
+                blk = dist[qoff[a]:qoff[a + 1], doff[b]:doff[b + 1]]
+                if blk.size:
+                    want_min[a, b] = blk.min()
+                    want_last[a, b] = blk[-1, -1]
+        mn, last = dct_sim.protein_scores(qf, qoff, df, doff, workspace_bytes=ws)
+        assert np.array_equal(mn, want_min) and np.array_equal(last, want_last)
+    # the listed-pairs scorer agrees where both proteins have fingerprints
+    cat = np.concatenate([qf, df])
+    off = np.concatenate([qoff, doff[1:] + qoff[-1]])
+    m1, l1 = dct_sim._pair_dists(cat, off, np.zeros(nd, dtype=np.int32), np.arange(nd, dtype=np.int32) + nq)
+    ok = want_min[0] < big
+    assert np.array_equal(m1[ok], want_min[0][ok]) and np.array_equal(l1[ok], want_last[0][ok])
 
 
 def test_properties_at_scale():
