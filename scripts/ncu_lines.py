@@ -14,16 +14,19 @@ from collections import defaultdict
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def line_table(obj, pattern):
+def line_table(obj, pattern, want_len=None):
     tmp = tempfile.mkdtemp()
     subprocess.run(['cuobjdump', '-xelf', 'all', os.path.join(ROOT, 'dctdomain_b200', 'libdctd.so')], cwd=tmp,
                    stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
     cubin = [f for f in os.listdir(tmp) if f.startswith(obj) and f.endswith('.cubin')][0]
     text = subprocess.run(['nvdisasm', '-g', '-c', os.path.join(tmp, cubin)], capture_output=True, text=True).stdout
-    out, inside, cur = [], False, ('?', 0)
+    funcs, out, inside, cur = [], None, False, ('?', 0)
     for ln in text.splitlines():
         if ln.startswith('//---') and '.text.' in ln:
             inside = re.search(pattern, ln) is not None
+            if inside:
+                out = []
+                funcs.append(out)
             continue
         if not inside:
             continue
@@ -34,7 +37,12 @@ def line_table(obj, pattern):
         m = re.match(r'\s*/\*([0-9a-f]{4,})\*/\s+(.*?);', ln)
         if m:
             out.append((int(m.group(1), 16), cur, m.group(2).strip()))
-    return out
+    # several instantiations may match the pattern: take the one with as many instructions as the report holds
+    if want_len is not None:
+        for f in funcs:
+            if len(f) == want_len:
+                return f
+    return funcs[0] if funcs else []
 
 
 def main():
@@ -47,7 +55,7 @@ def main():
     i_s, i_n = hdr.index('# Samples'), hdr.index('Instructions Executed')
     i_w, i_wi = hdr.index('L1 Wavefronts Shared'), hdr.index('L1 Wavefronts Shared Ideal')
     stall = {h: i for i, h in enumerate(hdr) if h.startswith('stall_') and 'Not Issued' not in h}
-    table = line_table(obj, pattern)
+    table = line_table(obj, pattern, len(data))
     if len(table) != len(data):
         print(f'warning: {len(table)} instructions in the cubin vs {len(data)} in the report', file=sys.stderr)
     agg = defaultdict(lambda: defaultdict(float))
