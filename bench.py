@@ -321,35 +321,57 @@ def run_ours(args):
     h2d = int(sum(2 * int(Ln) * D * 4 for Ln in elens))
     d2h = Be * LAYERS * QDIM[0] * QDIM[1]
 
-    def e2e_step():
-        fps = [Fingerprint(pid=pid, seq='', embed=emb, domains=[f'1-{Ln}'], quants={}) for pid, Ln, emb in host_fps]
-        quantize_batch(fps, QDIM, device=dev)
-        return fps
-
-    # context for e2e: what one big pinned H2D copy achieves on this box
+    # context for e2e: what one big pinned H2D copy achieves on this box - alone, and with every rank copying at once
     big = torch.empty(256 << 20, dtype=torch.uint8).pin_memory()
     dbig = torch.empty_like(big, device=dev)
     dbig.copy_(big, non_blocking=True)
     torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for _ in range(4):
-        dbig.copy_(big, non_blocking=True)
-    torch.cuda.synchronize()
-    link_gbps = 4 * big.numel() / (time.perf_counter() - t0) / 1e9
+
+    def link_rate():
+        t0 = time.perf_counter()
+        for _ in range(4):
+            dbig.copy_(big, non_blocking=True)
+        torch.cuda.synchronize()
+        return 4 * big.numel() / (time.perf_counter() - t0) / 1e9
+
+    link_gbps = link_rate()
+    link_all = None
+    if world > 1:
+        barrier()
+        mine = link_rate()                     # all ranks copy at the same time
+        t = torch.tensor([mine, -mine], dtype=torch.float64, device=dev)
+        tsum = torch.tensor([mine], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tsum)
+        link_all = {'per_rank_max': float(t[0].item()), 'per_rank_min': float(-t[1].item()), 'aggregate': float(tsum.item())}
     del big, dbig
+
+    def e2e_run(staging):
+        def one():
+            fps = [Fingerprint(pid=pid, seq='', embed=emb, domains=[f'1-{Ln}'], quants={}) for pid, Ln, emb in host_fps]
+            quantize_batch(fps, QDIM, device=dev, staging=staging)
+        for _ in range(2):
+            one()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            one()
+        barrier()
+        return max_over_ranks(time.perf_counter() - t0)
+
     e2e_steps = max(3, min(args.steps, 8))
-    for _ in range(2):
-        e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        fps = e2e_step()
-    barrier()
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_s = e2e_run('auto')
     e2e = {'value': Be * e2e_steps * world / e2e_s, 'unit': 'fingerprints/s', 'h2d_bytes_per_step': h2d,
            'd2h_bytes_per_step': d2h, 'steps': e2e_steps, 'domains_per_step': Be,
            'h2d_GBps_achieved': h2d * e2e_steps / e2e_s / 1e9, 'h2d_GBps_link_pinned_copy': link_gbps,
+           'h2d_GBps_link_all_ranks_copying': link_all,
            'api': 'dctdomain_b200.fingerprint.quantize_batch(list[Fingerprint]) with pinned host embeddings'}
+    if world > 1:
+        # the same through one copy-engine transfer per array instead of the gather kernel: which staging route shares
+        # the host's memory and PCIe root complexes better when every rank is copying
+        dma_s = e2e_run('dma')
+        e2e['staging_gather_vs_dma'] = {'gather_fingerprints_per_s': e2e['value'], 'dma_fingerprints_per_s': Be * e2e_steps * world / dma_s,
+                                        'per_rank_GBps_gather': h2d * e2e_steps / e2e_s / 1e9, 'per_rank_GBps_dma': h2d * e2e_steps / dma_s / 1e9}
 
     # ---- e2e with device-resident embeddings (the ESM-2 output never leaves the GPU) ----
     e2e_device = None

@@ -391,7 +391,7 @@ def _retire(device, plan):
 
 
 def quantize_batch(fps, qdim=(3, 80, 3, 80), device=None, maxlen=DEFAULT_MAXLEN, overlap=OVERLAP, plan_flags: int = 0,
-                   quants_dtype=np.int64, _timing=None):
+                   quants_dtype=np.int64, staging: str = 'auto', _timing=None):
     """``quantize`` for a list of Fingerprint-like objects in one kernel launch per (n, m) group.
 
     Each object needs ``embed`` ({layer: [L, D] array | list of window arrays}), ``domains`` (list of
@@ -400,7 +400,9 @@ def quantize_batch(fps, qdim=(3, 80, 3, 80), device=None, maxlen=DEFAULT_MAXLEN,
     device buffer with a single C call (one cudaMemcpyAsync per array); CUDA tensors are read in place.
     ``plan_flags``: per-call options of the work decomposition (``_lib.FP_PLAN_NO_FUSION`` ...).  ``quants_dtype``: dtype
     of the arrays put into ``quants`` - int64 is what the reference produces (``np.array`` of Python ints,
-    src/fingerprint.py:200); ``np.int8`` skips the widening (same values, an eighth of the bytes).  Returns the list.
+    src/fingerprint.py:200); ``np.int8`` skips the widening (same values, an eighth of the bytes).  ``staging``: how
+    pinned host arrays reach the device - 'auto' / 'gather' (one gather kernel pulling all arrays over PCIe) or 'dma' (one
+    copy-engine transfer per array, what pageable arrays always take).  Returns the list.
     """
     fps = list(fps)
     if not fps:
@@ -457,7 +459,7 @@ def quantize_batch(fps, qdim=(3, 80, 3, 80), device=None, maxlen=DEFAULT_MAXLEN,
             a_len = np.array(h_bytes[lo:], dtype=np.int64)
             a_off = np.array(h_off[lo:], dtype=np.int64)
             with torch.cuda.device(dev):
-                if all(h_pin[lo:]) and not (a_len % 16).any() and not (a_src % 16).any():     # 16-byte loads: sizes AND addresses
+                if staging != 'dma' and all(h_pin[lo:]) and not (a_len % 16).any() and not (a_src % 16).any():     # 16-byte loads: sizes AND addresses
                     # pinned sources: one gather kernel over <= 256 KB pieces (no per-array DMA gaps)
                     npc = (a_len + _GATHER_PIECE - 1) // _GATHER_PIECE
                     total = int(npc.sum())

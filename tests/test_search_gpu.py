@@ -333,3 +333,45 @@ def test_threshold_and_heap_paths_agree_at_scale():
     assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
     a = idx.search(q[:9], 50)
     assert np.array_equal(a[0], b[0][:9]) and np.array_equal(a[1], b[1][:9])
+
+
+def test_index_file_field_list_of_faiss_write_index(tmp_path):
+    """`.index` bytes against the field list of faiss 1.7.4 (impl/index_write.cpp): write_index(IndexFlat) writes the
+    fourcc ("IxF2" for METRIC_L2, "IxFI" inner product, "IxFl" otherwise), then write_index_header - d (int32), ntotal
+    (int64), two int64 dummies (1 << 20), is_trained (1 byte), metric_type (int32) and, only if metric_type > 1,
+    metric_arg (float32) - then WRITE_XBVECTOR(codes): the element count as uint64 in units of 4 bytes
+    (= ntotal * d floats) followed by the raw float32 rows.  No faiss-written file exists offline (faiss is not in the
+    image, the reference ships no .index), so this pins OUR reading of that list field by field with an independent
+    struct parser; read_index must accept exactly this layout for all three metrics."""
+    import struct
+    from dctdomain_b200 import index as dindex
+    db = synth.fingerprints(4, 77)
+    for cls, metric, fourcc, has_arg in ((dindex.IndexFlatL2, dindex.METRIC_L2, b'IxF2', False),
+                                         (dindex.IndexFlatL1, dindex.METRIC_L1, b'IxFl', True)):
+        idx = cls(480)
+        idx.add(db)
+        path = str(tmp_path / f'm{metric}.index')
+        dindex.write_index(idx, path)
+        raw = open(path, 'rb').read()
+        pos = 0
+        assert raw[:4] == fourcc
+        pos += 4
+        d, ntotal, dummy1, dummy2 = struct.unpack_from('<iqqq', raw, pos)
+        pos += 4 + 8 + 8 + 8
+        assert (d, ntotal, dummy1, dummy2) == (480, 77, 1 << 20, 1 << 20)
+        (is_trained,) = struct.unpack_from('<B', raw, pos)
+        pos += 1
+        (metric_type,) = struct.unpack_from('<i', raw, pos)
+        pos += 4
+        assert is_trained == 1 and metric_type == metric
+        if has_arg:
+            (metric_arg,) = struct.unpack_from('<f', raw, pos)
+            pos += 4
+            assert metric_arg == 0.0
+        (count,) = struct.unpack_from('<Q', raw, pos)
+        pos += 8
+        assert count == 77 * 480 and len(raw) == pos + count * 4
+        rows = np.frombuffer(raw, dtype='<f4', offset=pos).reshape(77, 480)
+        assert np.array_equal(rows, db.astype(np.float32))
+        back = dindex.read_index(path)
+        assert back.metric_type == metric and back.d == 480 and back.ntotal == 77 and np.array_equal(back.reconstruct_n(), db)
