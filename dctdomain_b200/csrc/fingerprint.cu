@@ -946,11 +946,11 @@ WsLayout make_ws_layout(int m, int max_smem) {
     w.DSo = std::min(2 * w.DSe, QQ);
     size_t off = 0;
     auto take = [&](size_t bytes) { const size_t o = off; off += dctd::align_up(bytes, 128); return (unsigned)o; };
-    w.off_bars = take((2 * kWsMaxStages + 4) * sizeof(unsigned long long));
+    w.off_bars = take((2 * kWsMaxStages + 2 * kWsMaxUBufs) * sizeof(unsigned long long));
     w.off_meta = take(kWsMaxStages * sizeof(int4));
     w.off_basis = take((size_t)kWsBasisRows * Cfg::KS * sizeof(float));
     w.off_desc = take((size_t)kWsDescSlots * 32 * sizeof(int));
-    w.off_u = take((size_t)2 * K * DC * sizeof(double));
+    w.off_u = take((size_t)Cfg::NB * K * DC * sizeof(double));
     w.off_ye = take((size_t)N * (DC / 2) * sizeof(float));
     w.off_yo = take((size_t)N * (DC / 2) * sizeof(float));
     w.off_f = take(((size_t)(w.DSo + w.DSe) * N * w.H + (size_t)N * nk + (size_t)N * m) * sizeof(double));

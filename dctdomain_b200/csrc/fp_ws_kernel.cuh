@@ -25,6 +25,7 @@ constexpr int kWsFinWarps = 8;
 constexpr int kWsFinThreads = kWsFinWarps * 32;
 constexpr int kWsDescSlots = 16;     // item records in flight between producer and finishers
 constexpr int kWsMaxStages = 10;
+constexpr int kWsMaxUBufs = 4;        // hand-over buffers between consumers and finishers (WsCfg::NB of them are used)
 constexpr int kWsBasisRows = 256;    // basis ring (rows); >= 32 + stages x rows per stage + 32, power of two
 
 // stage flags
@@ -62,6 +63,14 @@ struct WsCfg {
 #ifndef WS_FLUSH_ROWS_RIDER
 #define WS_FLUSH_ROWS_RIDER WS_FLUSH_ROWS
 #endif
+#ifndef WS_UBUFS
+#define WS_UBUFS 2
+#endif
+#ifndef WS_UBUFS_RIDER
+#define WS_UBUFS_RIDER WS_UBUFS
+#endif
+    static constexpr int NB = RIDER ? WS_UBUFS_RIDER : WS_UBUFS;      // hand-over buffers (each K * D doubles)
+    static_assert(NB >= 2 && NB <= kWsMaxUBufs, "hand-over buffers");
     static constexpr int FLUSH_ROWS = RIDER ? WS_FLUSH_ROWS_RIDER : WS_FLUSH_ROWS;   // float32 chain length of pass 1
     static constexpr int FLUSH_EVERY = (FLUSH_ROWS / R) < 1 ? 1 : (FLUSH_ROWS / R);
     static_assert(DC % 128 == 0, "one consumer warp per 128 columns (and float4 steps over D/4 columns)");
@@ -117,20 +126,20 @@ __global__ void __launch_bounds__(WsCfg<K, DC, RIDER>::T, 1) fp_ws_kernel(const 
     const int NST = wl.nst;
     unsigned long long *full = reinterpret_cast<unsigned long long *>(smem + wl.off_bars);   // [NST]
     unsigned long long *empty = full + kWsMaxStages;                                        // [NST]
-    unsigned long long *u_full = empty + kWsMaxStages;                                      // [2]
-    unsigned long long *u_empty = u_full + 2;                                               // [2]
+    unsigned long long *u_full = empty + kWsMaxStages;                                      // [NB]
+    unsigned long long *u_empty = u_full + kWsMaxUBufs;                                     // [NB]
     int4 *metas = reinterpret_cast<int4 *>(smem + wl.off_meta);            // [NST] {nrows, flags, desc slot | basis slot << 8, rider slab}
     float *basis = reinterpret_cast<float *>(smem + wl.off_basis);         // [kWsBasisRows][KS] ring
     int *desc = reinterpret_cast<int *>(smem + wl.off_desc);               // [kWsDescSlots][32]
     unsigned char *ring = smem + wl.off_ring;                              // [NST][STAGE_BYTES]
-    double *ubuf = reinterpret_cast<double *>(smem + wl.off_u);            // [2][K][D]
+    double *ubuf = reinterpret_cast<double *>(smem + wl.off_u);            // [NB][K][D]
     float *Ye = reinterpret_cast<float *>(smem + wl.off_ye);               // [2][N][D/4]  EE | EO (see stage1)
     float *Yo = reinterpret_cast<float *>(smem + wl.off_yo);               // [2][N][D/4]  OD | OR
     double *Fs = reinterpret_cast<double *>(smem + wl.off_f);              // pass-2a partial sums | Fr [N][nk] | Z [N][m]
     float *TT = reinterpret_cast<float *>(smem + wl.off_tt);               // [even i | odd i] halves of cos(pi (i mod 4D) / 2D), i < 4D + 8m
     double *Tm = reinterpret_cast<double *>(smem + wl.off_tm);             // cos(pi i / 2m), i < 4m
     double *Mj = reinterpret_cast<double *>(smem + wl.off_mj);             // [N][K] cos(pi (2j+1) k / 2n)
-    __shared__ int u_slot[2];
+    __shared__ int u_slot[kWsMaxUBufs];
     __shared__ int s_flag, s_last, s_rlast;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -138,7 +147,7 @@ __global__ void __launch_bounds__(WsCfg<K, DC, RIDER>::T, 1) fp_ws_kernel(const 
 
     if (tid == 0) {
         for (int s = 0; s < NST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], NCW); }
-        for (int b = 0; b < 2; ++b) { mbar_init(&u_full[b], NCW); mbar_init(&u_empty[b], 1); }
+        for (int b = 0; b < Cfg::NB; ++b) { mbar_init(&u_full[b], NCW); mbar_init(&u_empty[b], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     // cos(pi i / 2D) split by the parity of i: odd k only ever look up odd i = (2d+1) k, even k even i, and inside
@@ -423,7 +432,7 @@ __global__ void __launch_bounds__(WsCfg<K, DC, RIDER>::T, 1) fp_ws_kernel(const 
                 if (ctid == 0) u_slot[ub] = mt.z & 255;
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&u_full[ub]);
-                if (++ub == 2) { ub = 0; uph ^= 1u; }
+                if (++ub == Cfg::NB) { ub = 0; uph ^= 1u; }
 #pragma unroll
                 for (int k = 0; k < KS; ++k)
 #pragma unroll
@@ -775,7 +784,7 @@ __global__ void __launch_bounds__(WsCfg<K, DC, RIDER>::T, 1) fp_ws_kernel(const 
                 }
             }
             if (ftid == 0) mbar_arrive(&u_empty[fb]);      // every finisher thread is done with ubuf[fb]
-            if (++fb == 2) { fb = 0; fph ^= 1u; }
+            if (++fb == Cfg::NB) { fb = 0; fph ^= 1u; }
             if (rider_last) finish_rest(ds_[kWRiderDom], layer);
             else if (own_ready) finish_rest(dom, layer);
             else fin_bar();                                 // s_last / s_rlast are rewritten by the next iteration
