@@ -1009,6 +1009,12 @@ int launch_ws(const dctd_fp_plan *plan, Params &prm, int max_smem, int n_sm, cud
     return DCTD_OK;
 }
 
+template <int DC>
+int launch_ws_d(const dctd_fp_plan *plan, Params &prm, int max_smem, int n_sm, cudaStream_t stream, bool *launched) {
+    return plan->has_rider ? launch_ws<2, DC, true>(plan, prm, max_smem, n_sm, stream, launched)
+                           : launch_ws<2, DC, false>(plan, prm, max_smem, n_sm, stream, launched);
+}
+
 }  // namespace
 
 extern "C" {
@@ -1469,18 +1475,19 @@ int dctd_fp_execute(const dctd_fp_plan *plan, const void *const *h_src_ptrs, int
     prm.wsitems = (const int32_t *)(ws + plan->off_wsitems);
 
     const int K = plan->n - 1;
-    // The reference's configuration (n = 3; ESM-2 t33 / t30 widths, contiguous rows) runs on the warp-specialised
-    // TMA kernel; every other shape on the general kernel below.  g_variant == 9 forces the general kernel (A/B runs).
-    if (vec4 && ld == plan->D && K == 2 && g_variant != 9 && !(plan->flags & DCTD_FP_PLAN_GENERAL_KERNEL) &&
-        (plan->D == 1280 || plan->D == 640)) {
+    // The reference's configuration (n = 3, contiguous rows) at the ESM-2 / ProtT5 widths runs on the warp-specialised
+    // TMA kernel; every other shape on the general kernel below.
+    if (vec4 && ld == plan->D && K == 2 && g_variant != 9 && !(plan->flags & DCTD_FP_PLAN_GENERAL_KERNEL)) {
         bool launched = false;
-        int rc;
-        if (plan->D == 1280)
-            rc = plan->has_rider ? launch_ws<2, 1280, true>(plan, prm, max_smem, n_sm, stream, &launched)
-                                 : launch_ws<2, 1280, false>(plan, prm, max_smem, n_sm, stream, &launched);
-        else
-            rc = plan->has_rider ? launch_ws<2, 640, true>(plan, prm, max_smem, n_sm, stream, &launched)
-                                 : launch_ws<2, 640, false>(plan, prm, max_smem, n_sm, stream, &launched);
+        int rc = DCTD_OK;
+        switch (plan->D) {       // ESM-2 t33 / t30 / t12 and ProtT5.  (D = 320, ESM-2 t6: measured slower than the
+                                 // general kernel - 4270 vs 4600 GB/s: at 1280 bytes per row every item is finisher-bound)
+            case 1280: rc = launch_ws_d<1280>(plan, prm, max_smem, n_sm, stream, &launched); break;
+            case 640: rc = launch_ws_d<640>(plan, prm, max_smem, n_sm, stream, &launched); break;
+            case 1024: rc = launch_ws_d<1024>(plan, prm, max_smem, n_sm, stream, &launched); break;
+            case 480: rc = launch_ws_d<480>(plan, prm, max_smem, n_sm, stream, &launched); break;
+            default: break;
+        }
         if (rc != DCTD_OK || launched) return rc;
     }
     KernelFn fn = nullptr;

@@ -49,7 +49,7 @@ template <int K, int DC, bool RIDER>
 struct WsCfg {
     static constexpr int KS = RIDER ? 2 * K : K;
     static constexpr int NCT = DC / 4;                  // consumer threads: one per float4 column group
-    static constexpr int NCW = NCT / 32;
+    static constexpr int NCW = (NCT + 31) / 32;         // the last consumer warp may be partly idle (D = 320 / 480)
 #ifndef WS_STAGE_ROW_BYTES
 #define WS_STAGE_ROW_BYTES 5120
 #endif
@@ -73,7 +73,7 @@ struct WsCfg {
     static_assert(NB >= 2 && NB <= kWsMaxUBufs, "hand-over buffers");
     static constexpr int FLUSH_ROWS = RIDER ? WS_FLUSH_ROWS_RIDER : WS_FLUSH_ROWS;   // float32 chain length of pass 1
     static constexpr int FLUSH_EVERY = (FLUSH_ROWS / R) < 1 ? 1 : (FLUSH_ROWS / R);
-    static_assert(DC % 128 == 0, "one consumer warp per 128 columns (and float4 steps over D/4 columns)");
+    static_assert(DC % 16 == 0, "float4 steps over the D/4 folded columns of pass 2a");
     static_assert(R % 2 == 0, "dual stages hold R/2 rows of each window");
 };
 
@@ -291,8 +291,11 @@ __global__ void __launch_bounds__(WsCfg<K, DC, RIDER>::T, 1) fp_ws_kernel(const 
     } else if (warp <= NCW) {
         // =============================== consumers ===============================
         const int ctid = tid - 32;
-        const int col = ctid * 4;
-        const unsigned int ring_u32 = smem_u32(ring) + (unsigned int)ctid * 16u;
+        // D not a multiple of 128: the lanes of the last consumer warp beyond the last column group run along with
+        // column group 0 (same loads, no stores), so that every warp-level step stays uniform
+        const bool c_active = ctid < Cfg::NCT;
+        const int col = (c_active ? ctid : 0) * 4;
+        const unsigned int ring_u32 = smem_u32(ring) + (unsigned int)col * 4u;
         int s = 0, ub = 0, nflush = 0;
         unsigned int fph = 0, uph = 1;
         double acc[KS][4];
@@ -411,13 +414,15 @@ __global__ void __launch_bounds__(WsCfg<K, DC, RIDER>::T, 1) fp_ws_kernel(const 
                 WS_WAIT(&u_empty[ub], uph, 2);
                 WS_ACC(t_u);
                 double *u = ubuf + (size_t)ub * K * D;
+                if (c_active) {
 #pragma unroll
-                for (int k = 0; k < K; ++k) {
-                    *reinterpret_cast<double2 *>(u + k * D + col) = make_double2(acc[k][0], acc[k][1]);
-                    *reinterpret_cast<double2 *>(u + k * D + col + 2) = make_double2(acc[k][2], acc[k][3]);
+                    for (int k = 0; k < K; ++k) {
+                        *reinterpret_cast<double2 *>(u + k * D + col) = make_double2(acc[k][0], acc[k][1]);
+                        *reinterpret_cast<double2 *>(u + k * D + col + 2) = make_double2(acc[k][2], acc[k][3]);
+                    }
                 }
                 if constexpr (RIDER) {
-                    if (flags & kStRider) {     // the rider's partial sums go straight to its workspace slab
+                    if ((flags & kStRider) && c_active) {     // the rider's partial sums go straight to its workspace slab
                         double *slab = p.partials + (int64_t)mt.w * (K * D);
 #pragma unroll
                         for (int k = 0; k < K; ++k) {

@@ -100,9 +100,12 @@ class _Plan:
         self.n_items = int(L.dctd_fp_num_items(self.handle))
 
     def __del__(self):
-        if getattr(self, 'handle', None) and self.handle.value:
-            _lib.lib().dctd_fp_plan_destroy(self.handle)
-            self.handle = C.c_void_p()
+        try:
+            if getattr(self, 'handle', None) and self.handle.value:
+                _lib.lib().dctd_fp_plan_destroy(self.handle)
+                self.handle = C.c_void_p()
+        except Exception:       # interpreter shutdown: the module globals may be gone already
+            pass
 
 
 def _i32(a):

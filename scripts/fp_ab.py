@@ -141,6 +141,9 @@ def main():
     domains(n_dom, 640, variants, res)
     domains(n_dom * 2, 1280, variants, res, lo=40, hi=120)
     windows(max(64, n_dom // 8), 1280, variants, res)
+    for D in (1024, 480, 320):       # ProtT5 / ESM-2 t12 / t6 widths
+        domains(n_dom, D, variants, res)
+    proteins(n_dom // 2, 480, variants, res)
     os.makedirs('gpurun_out', exist_ok=True)
     json.dump(res, open('gpurun_out/fp_ab.json', 'w'), indent=1)
 

@@ -255,7 +255,7 @@ def test_protein_level_fusion_on_and_off():
 
 
 @pytest.mark.parametrize('seed', [0, 1, 2, 3])
-@pytest.mark.parametrize('D', [1280, 640])
+@pytest.mark.parametrize('D', [1280, 640, 1024, 480])
 def test_geometry_fuzz_warp_specialised_vs_general_kernel(seed, D):
     """Random batch geometry - short and long proteins, maxlen windows, discontinuous / overlapping / unsorted
     domains, global domains with and without fusion partners, domains long enough to be split over items - run through
@@ -333,6 +333,11 @@ def test_geometry_fuzz_warp_specialised_vs_general_kernel(seed, D):
         assert all(np.array_equal(runs[0], r) for r in runs[1:]), f'variant {variant} is not reproducible'
         outs[variant] = runs[0].astype(int)
     assert np.array_equal(outs[0], outs[4])
-    diff = np.abs(outs[0] - outs[9])
+    # A domain that lists the same segment twice is x = [A; A]: its k = 2 projection vanishes identically
+    # (cos t + cos(t + pi) = 0), so the middle output row is the min-max of rounding noise - in the reference too.
+    # Such rows are decided by 1e-16 effects in every implementation and are left out of the comparison.
+    ill = [i for i in range(nd) if len(set(zip(sb[seg_off[i]:seg_off[i + 1]], se[seg_off[i]:seg_off[i + 1]]))) < seg_off[i + 1] - seg_off[i]]
+    keep = np.setdiff1d(np.arange(nd), ill)
+    diff = np.abs(outs[0] - outs[9])[keep]
     assert diff.max() <= 1, np.argwhere(diff > 1)[:5]
     assert (diff != 0).mean() <= TOL_FRAC, (int((diff != 0).sum()), diff.size)
