@@ -95,6 +95,7 @@ struct Params {
     int *counters;
     double *partials;
     long long *timing;      // [16] phase cycle counters (DCTD_FP_TIMING builds only)
+    double *debug_u;        // DCTD_DEBUG_U builds: per (domain, layer, split) copy of the consumers' sums
     int8_t *out;
     int64_t ld, out_stride;
     int32_t n_src, n_items, n_layers;
@@ -799,6 +800,9 @@ __global__ void __launch_bounds__(MAXT, MINB) fp_kernel(const Params p) {
 // ------------------------------------------------------------------------------------------
 // host: layout, planner, launch
 // ------------------------------------------------------------------------------------------
+#ifdef DCTD_DEBUG_U
+double *g_debug_u = nullptr;
+#endif
 #ifdef DCTD_TUNING
 // process-global A/B switches: tuning builds only (libdctd_tuning.so, dctd_fp_set_variant).  The release library has
 // no mutable global state: per-plan options travel in the flags of dctd_fp_plan_create_ex.
@@ -955,7 +959,7 @@ WsLayout make_ws_layout(int m, int max_smem) {
     w.off_yo = take((size_t)N * (DC / 2) * sizeof(float));
     w.off_f = take(((size_t)(w.DSo + w.DSe) * N * w.H + (size_t)N * nk + (size_t)N * m) * sizeof(double));
     w.off_tt = take((size_t)(4 * DC + 8 * m) * sizeof(float));
-    w.off_tm = take((size_t)4 * m * sizeof(double));
+    w.off_tm = take((size_t)(4 * m + (4 * m >> 4) + 1) * sizeof(double));     // skewed: entry i at i + (i >> 4)
     w.off_mj = take((size_t)N * K * sizeof(double));
     w.off_ring = take(0);
     const long long room = (long long)max_smem - (long long)off - 1024;      // 1 KB for the static shared variables
@@ -1384,10 +1388,10 @@ int dctd_fp_set_variant(int v) {
 /* DCTD_FP_TIMING builds: copies the 16 per-phase cycle counters of the last dctd_fp_execute on this
  * workspace to the host (synchronises the device) */
 int dctd_fp_timing_read(const dctd_fp_plan *plan, const void *d_workspace, int64_t *h_out16) {
-#ifdef DCTD_FP_TIMING
+#if defined(DCTD_FP_TIMING) || defined(DCTD_DEBUG_U)
     if (!plan || !d_workspace || !h_out16) return DCTD_ERR_ARG;
     DCTD_CUDA_TRY(cudaDeviceSynchronize());
-    DCTD_CUDA_TRY(cudaMemcpy(h_out16, (const char *)d_workspace + plan->off_timing, 128, cudaMemcpyDeviceToHost));
+    DCTD_CUDA_TRY(cudaMemcpy(h_out16, (const char *)d_workspace + plan->off_timing, 256, cudaMemcpyDeviceToHost));
     return DCTD_OK;
 #else
     (void)plan; (void)d_workspace; (void)h_out16;
@@ -1406,6 +1410,9 @@ int dctd_fp_plan_dump(const dctd_fp_plan *plan, int32_t *pieces, int64_t max_pie
     return DCTD_OK;
 }
 
+#ifdef DCTD_DEBUG_U
+void *dctd_fp_debug_u(void) { return g_debug_u; }
+#endif
 /* introspection: copies the 32-word item records of the warp-specialised kernel (same order as the items) */
 int dctd_fp_plan_dump_records(const dctd_fp_plan *plan, int32_t *records, int64_t max_items) {
     if (!plan || !records || max_items < 0) return DCTD_ERR_ARG;
@@ -1452,7 +1459,7 @@ int dctd_fp_execute(const dctd_fp_plan *plan, const void *const *h_src_ptrs, int
     }
     DCTD_CUDA_TRY(cudaMemcpyAsync(ws + plan->off_src, h_src_ptrs, nptr * sizeof(void *), cudaMemcpyHostToDevice, stream));
     DCTD_CUDA_TRY(cudaMemsetAsync(ws + plan->off_counters, 0, (size_t)plan->n_counters * sizeof(int), stream));
-#ifdef DCTD_FP_TIMING
+#if defined(DCTD_FP_TIMING) || defined(DCTD_DEBUG_U)
     DCTD_CUDA_TRY(cudaMemsetAsync(ws + plan->off_timing, 0, 256, stream));
 #endif
 
@@ -1464,6 +1471,16 @@ int dctd_fp_execute(const dctd_fp_plan *plan, const void *const *h_src_ptrs, int
     prm.counters = (int *)(ws + plan->off_counters);
     prm.partials = (double *)(ws + plan->off_partials);
     prm.timing = (long long *)(ws + plan->off_timing);
+#ifdef DCTD_DEBUG_U
+    {
+        static double *dbg = nullptr;
+        static size_t dbg_bytes = 0;
+        const size_t need = (size_t)plan->n_dom * plan->n_layers * 4 * (plan->n - 1) * plan->D * sizeof(double);
+        if (need > dbg_bytes) { if (dbg) cudaFree(dbg); cudaMalloc(&dbg, need); dbg_bytes = need; }
+        prm.debug_u = dbg;
+        g_debug_u = dbg;
+    }
+#endif
     prm.out = d_out;
     prm.ld = ld;
     prm.out_stride = out_stride;

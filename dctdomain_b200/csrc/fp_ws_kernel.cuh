@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(WsCfg<K, DC, RIDER>::T, 1) fp_ws_kernel(const 
     float *Yo = reinterpret_cast<float *>(smem + wl.off_yo);               // [2][N][D/4]  OD | OR
     double *Fs = reinterpret_cast<double *>(smem + wl.off_f);              // pass-2a partial sums | Fr [N][nk] | Z [N][m]
     float *TT = reinterpret_cast<float *>(smem + wl.off_tt);               // [even i | odd i] halves of cos(pi (i mod 4D) / 2D), i < 4D + 8m
-    double *Tm = reinterpret_cast<double *>(smem + wl.off_tm);             // cos(pi i / 2m), i < 4m
+    double *Tm = reinterpret_cast<double *>(smem + wl.off_tm);             // cos(pi i / 2m), i < 4m, skewed (see below)
     double *Mj = reinterpret_cast<double *>(smem + wl.off_mj);             // [N][K] cos(pi (2j+1) k / 2n)
     __shared__ int u_slot[kWsMaxUBufs];
     __shared__ int s_flag, s_last, s_rlast;
@@ -153,7 +153,10 @@ __global__ void __launch_bounds__(WsCfg<K, DC, RIDER>::T, 1) fp_ws_kernel(const 
     // cos(pi i / 2D) split by the parity of i: odd k only ever look up odd i = (2d+1) k, even k even i, and inside
     // one parity class lanes with consecutive k are an odd number of entries apart (conflict-free)
     for (int i = tid; i < 4 * D + 8 * m; i += blockDim.x) TT[(i & 1) * (2 * D + 4 * m) + (i >> 1)] = __ldg(p.table + i);
-    for (int i = tid; i < 4 * m; i += blockDim.x) Tm[i] = cospi((double)i / (2.0 * m));
+    // cos(pi i / 2m) for pass 2b, entry i stored at i + (i >> 4): the lanes of a warp look up (2c + 1) k for 16 consecutive
+    // c, i.e. at a stride of 2k entries, and for k = 8, 16, ... all of them would meet in one bank of a plain table
+    for (int i = tid; i < 4 * m; i += blockDim.x) Tm[i + (i >> 4)] = cospi((double)i / (2.0 * m));
+    if (tid == 0) s_flag = 0;
     for (int i = tid; i < N * K; i += blockDim.x) {
         const int j = i / K, k = i % K + 1;
         Mj[i] = cospi((double)((2 * j + 1) * k) / (2.0 * N));
@@ -308,6 +311,9 @@ __global__ void __launch_bounds__(WsCfg<K, DC, RIDER>::T, 1) fp_ws_kernel(const 
             for (int v = 0; v < 4; ++v) acc[k][v] = 0.0;
         }
         pk2 npiv0 = zero, npiv1 = zero;
+#ifdef DCTD_DEBUG_U
+        pk2 chk0 = zero, chk1 = zero, chkx0 = zero, chkx1 = zero;
+#endif
         long long t_full = 0, t_u = 0, t_busy = 0;
         (void)t_full; (void)t_u; (void)t_busy;
         WS_T0();
@@ -336,7 +342,7 @@ __global__ void __launch_bounds__(WsCfg<K, DC, RIDER>::T, 1) fp_ws_kernel(const 
             if (++s == NST) { s = 0; fph ^= 1u; }
             if (nrows == R && !(flags & (kStDual | kStPivotOnly))) {
                 // the common stage: R rows of one source.  Straight-line code: every load is issued before the
-                // first use, and the stage goes back to the producer as soon as the loads have been performed
+                // first use, and the stage goes back to the producer as soon as the loads have been PERFORMED
                 // (the basis ring is not part of the stage: its slots are recycled 256 rows later, see the producer)
                 // Without a rider all basis values are fetched up front as well (measured: +2 % at D = 1280, +6 % at
                 // D = 640); with a rider (twice the projections) that would spill, so they are fetched row by row.
@@ -347,16 +353,29 @@ __global__ void __launch_bounds__(WsCfg<K, DC, RIDER>::T, 1) fp_ws_kernel(const 
                     for (int r = 0; r < R; ++r)
                         load_basis<KS>(basis + (size_t)((bslot + r) & (kWsBasisRows - 1)) * KS, c[r]);
                 }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&empty[s_cur]);
                 if (flags & kStPivotInline) {
                     npiv0 = mul2(x0[0], neg);
                     npiv1 = mul2(x1[0], neg);
                 }
+                // The pivot subtraction comes BEFORE the stage is handed back: it reads every register the stage's loads
+                // write, so the loads have been performed when the release is issued.  (Releasing right after ISSUING
+                // the loads let the refill of the slot overtake them under shared-memory pressure: 1 launch in 5 of the
+                // protein-shaped batch had a few hundred bytes of one (domain, layer) off - found by scripts/fp_check.py.)
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    x0[r] = add2(x0[r], npiv0);
+                    x1[r] = add2(x1[r], npiv1);
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[s_cur]);
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
                     if constexpr (RIDER) load_basis<KS>(basis + (size_t)((bslot + r) & (kWsBasisRows - 1)) * KS, c[0]);
-                    const pk2 t0 = add2(x0[r], npiv0), t1 = add2(x1[r], npiv1);
+                    const pk2 t0 = x0[r], t1 = x1[r];
+#ifdef DCTD_DEBUG_U
+                    chk0 = add2(chk0, t0); chk1 = add2(chk1, t1);
+                    chkx0 = add2(chkx0, c[RIDER ? 0 : r][0]); chkx1 = add2(chkx1, c[RIDER ? 0 : r][1]);
+#endif
 #pragma unroll
                     for (int k = 0; k < KS; ++k) {
                         a0[k] = fma2(t0, c[RIDER ? 0 : r][k], a0[k]);
@@ -383,6 +402,10 @@ __global__ void __launch_bounds__(WsCfg<K, DC, RIDER>::T, 1) fp_ws_kernel(const 
                             const pk2 t0 = add2(x0[r], npiv0), t1 = add2(x1[r], npiv1);
                             pk2 c[KS];
                             load_basis<KS>(basis + (size_t)((bslot + r) & (kWsBasisRows - 1)) * KS, c);
+#ifdef DCTD_DEBUG_U
+                            chk0 = add2(chk0, t0); chk1 = add2(chk1, t1);
+                            chkx0 = add2(chkx0, c[0]); chkx1 = add2(chkx1, c[1]);
+#endif
 #pragma unroll
                             for (int k = 0; k < KS; ++k) {
                                 a0[k] = fma2(t0, c[k], a0[k]);
@@ -415,10 +438,18 @@ __global__ void __launch_bounds__(WsCfg<K, DC, RIDER>::T, 1) fp_ws_kernel(const 
                 WS_ACC(t_u);
                 double *u = ubuf + (size_t)ub * K * D;
                 if (c_active) {
+                    // a thread owns 32 bytes per row; lanes 4..7 of every eight write their second half first so that the
+                    // eight 16-byte stores of a quarter warp fall into eight different bank groups
+#ifdef WS_OLD_STORE
+                    const int hx = 0;
+#else
+                    const int hx = (lane >> 2) & 1;
+#endif
 #pragma unroll
                     for (int k = 0; k < K; ++k) {
-                        *reinterpret_cast<double2 *>(u + k * D + col) = make_double2(acc[k][0], acc[k][1]);
-                        *reinterpret_cast<double2 *>(u + k * D + col + 2) = make_double2(acc[k][2], acc[k][3]);
+                        const double2 lo = make_double2(acc[k][0], acc[k][1]), hi = make_double2(acc[k][2], acc[k][3]);
+                        *reinterpret_cast<double2 *>(u + k * D + col + 2 * hx) = hx ? hi : lo;
+                        *reinterpret_cast<double2 *>(u + k * D + col + 2 - 2 * hx) = hx ? lo : hi;
                     }
                 }
                 if constexpr (RIDER) {
@@ -434,6 +465,24 @@ __global__ void __launch_bounds__(WsCfg<K, DC, RIDER>::T, 1) fp_ws_kernel(const 
                         // atomicAdd, and that release is cumulative over everything ordered before it
                     }
                 }
+#ifdef DCTD_DEBUG_U
+                if (c_active) {
+                    const int *dd = desc + (mt.z & 255) * 32;
+                    double *dbg = p.debug_u + ((size_t)(dd[kWDom] * p.n_layers + dd[kWLayer]) * 4 + min(dd[kWSplit], 3)) * (K * D);
+#pragma unroll
+                    for (int k = 0; k < K; ++k)
+#pragma unroll
+                        for (int v = 0; v < 4; ++v) dbg[k * D + col + v] = acc[k][v];
+                    // checksums: plain float32 sums of (x - pivot) per column (slot 2) and of the two basis values (slot 3)
+                    float c0, c1, c2, c3;
+                    unpk(chk0, c0, c1); unpk(chk1, c2, c3);
+                    double *d2 = dbg + (size_t)(2 - min(dd[kWSplit], 3)) * (K * D);
+                    if (dd[kWSplit] == 0) { d2[col] = c0; d2[col + 1] = c1; d2[col + 2] = c2; d2[col + 3] = c3; }
+                    unpk(chkx0, c0, c1); unpk(chkx1, c2, c3);
+                    if (dd[kWSplit] == 0) { d2[D + col] = c0; d2[D + col + 1] = c1; d2[D + col + 2] = c2; d2[D + col + 3] = c3; }
+                }
+                chk0 = zero; chk1 = zero; chkx0 = zero; chkx1 = zero;
+#endif
                 if (ctid == 0) u_slot[ub] = mt.z & 255;
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&u_full[ub]);
@@ -635,6 +684,11 @@ __global__ void __launch_bounds__(WsCfg<K, DC, RIDER>::T, 1) fp_ws_kernel(const 
                 Fr[i] = f;
             }
             fin_bar();
+            // everyone has read s_flag (layer_bad): reset it for the next stage 1, which no thread reaches before the
+            // barrier after pass 2b
+#ifndef WS_OLD_TICKET
+            if (ftid == 0) s_flag = 0;
+#endif
             WS_ACC(t_red);
             // ---- pass 2b: Z[j][c] = sum_k cos(pi (2c+1) k / 2m) F[j][k].  cos(pi (2(m-1-c)+1) k / 2m) =
             //      (-1)^k cos(pi (2c+1) k / 2m), so columns c and m-1-c share their products: with E / O the sums over
@@ -654,14 +708,14 @@ __global__ void __launch_bounds__(WsCfg<K, DC, RIDER>::T, 1) fp_ws_kernel(const 
                     int idx = stepc * k;                 // < 4m
                     double z0 = 0.0, z1 = 0.0;
                     for (; k + 2 <= nk; k += 4) {
-                        z0 = fma(Tm[idx], fr[k - 1], z0);
+                        z0 = fma(Tm[idx + (idx >> 4)], fr[k - 1], z0);
                         idx += step2;
                         if (idx >= m4) idx -= m4;
-                        z1 = fma(Tm[idx], fr[k + 1], z1);
+                        z1 = fma(Tm[idx + (idx >> 4)], fr[k + 1], z1);
                         idx += step2;
                         if (idx >= m4) idx -= m4;
                     }
-                    if (k <= nk) z0 = fma(Tm[idx], fr[k - 1], z0);
+                    if (k <= nk) z0 = fma(Tm[idx + (idx >> 4)], fr[k - 1], z0);
                     sum = z0 + z1;
                 }
                 const double other = __shfl_xor_sync(0xffffffffu, sum, 1);
@@ -708,16 +762,33 @@ __global__ void __launch_bounds__(WsCfg<K, DC, RIDER>::T, 1) fp_ws_kernel(const 
             double sacc[EPT];
 #pragma unroll
             for (int e = 0; e < EPT; ++e) sacc[e] = 0.0;
-            for (int sp = 0; sp < nsl; ++sp) {
-                const double *row = slab + (int64_t)sp * (K * D);
-                double v[EPT];
+            // two slab rows in flight (the adds stay in slot order)
+            int sp = 0;
+#ifndef WS_DBG_SLAB
+            for (; sp + 2 <= nsl; sp += 2) {
+                const double *row0 = slab + (int64_t)sp * (K * D), *row1 = row0 + K * D;
+                double v0[EPT], v1[EPT];
 #pragma unroll
                 for (int e = 0; e < EPT; ++e) {
                     const int i = ftid + e * NFT;
-                    v[e] = (i < K * D) ? __ldcg(row + i) : 0.0;
+                    v0[e] = (i < K * D) ? __ldcg(row0 + i) : 0.0;
                 }
 #pragma unroll
-                for (int e = 0; e < EPT; ++e) sacc[e] += v[e];
+                for (int e = 0; e < EPT; ++e) {
+                    const int i = ftid + e * NFT;
+                    v1[e] = (i < K * D) ? __ldcg(row1 + i) : 0.0;
+                }
+#pragma unroll
+                for (int e = 0; e < EPT; ++e) sacc[e] = (sacc[e] + v0[e]) + v1[e];
+            }
+#endif
+            for (; sp < nsl; ++sp) {
+                const double *row = slab + (int64_t)sp * (K * D);
+#pragma unroll
+                for (int e = 0; e < EPT; ++e) {
+                    const int i = ftid + e * NFT;
+                    sacc[e] += (i < K * D) ? __ldcg(row + i) : 0.0;
+                }
             }
 #pragma unroll
             for (int e = 0; e < EPT; ++e) {
@@ -734,20 +805,40 @@ __global__ void __launch_bounds__(WsCfg<K, DC, RIDER>::T, 1) fp_ws_kernel(const 
             WS_ACC(t_idle);
             const int slot = u_slot[fb];
             if (slot < 0) break;
+#ifdef WS_NOFIN
+            fin_bar();
+            if (ftid == 0) mbar_arrive(&u_empty[fb]);
+            if (++fb == Cfg::NB) { fb = 0; fph ^= 1u; }
+            continue;
+#endif
             const int *ds_ = desc + slot * 32;
             const int dom = ds_[kWDom], layer = ds_[kWLayer], iflags = ds_[kWFlags];
             double *u = ubuf + (size_t)fb * K * D;
+            // The rider ticket is taken by one thread of the last finisher warp (the warp with the least stage-1 work) and
+            // only looked at after stage 1: the fence, the atomic's round trip to L2 and stage 1 overlap, and no barrier
+            // is needed before stage 1 (s_flag is reset inside finish_rest, s_rlast is written after stage 1).
+            // The consumers wrote this item's rider sums to the slab before the hand-over through the CTA-scope mbarrier;
+            // the release at GPU scope needs the fence in the thread that takes the ticket.
+            int ticket = -1;
+#ifdef WS_OLD_TICKET
+            const bool ticket_thread = false;
             if (ftid == 0) {
                 s_flag = 0;
                 s_rlast = 0;
                 if (RIDER && (iflags & kWfRider)) {
-                    // the consumers wrote this item's rider sums to the slab (and fenced) before the hand-over through the
-                    // CTA-scope mbarrier; the release at GPU scope needs the fence in the thread that takes the ticket
                     __threadfence();
-                    const int ticket = atomicAdd(&p.counters[ds_[kWRiderCounter]], 1);
-                    s_rlast = (ticket == ds_[kWRiderNsplit] - 1);
+                    const int t0 = atomicAdd(&p.counters[ds_[kWRiderCounter]], 1);
+                    s_rlast = (t0 == ds_[kWRiderNsplit] - 1);
                 }
             }
+            if (!(iflags & kWfSplit)) fin_bar();
+#else
+            const bool ticket_thread = RIDER && ftid == NFT - 32 && (iflags & kWfRider);
+            if (ticket_thread) {
+                __threadfence();
+                ticket = atomicAdd(&p.counters[ds_[kWRiderCounter]], 1);
+            }
+#endif
             bool own_ready = true;
             if (iflags & kWfSplit) {
                 // a domain assembled from several items: publish this item's sums, the last to arrive adds them up
@@ -758,8 +849,8 @@ __global__ void __launch_bounds__(WsCfg<K, DC, RIDER>::T, 1) fp_ws_kernel(const 
                 __threadfence();
                 fin_bar();
                 if (ftid == 0) {
-                    const int ticket = atomicAdd(&p.counters[ds_[kWCounter]], 1);
-                    s_last = (ticket == nsplit - 1);
+                    const int t2 = atomicAdd(&p.counters[ds_[kWCounter]], 1);
+                    s_last = (t2 == nsplit - 1);
                 }
                 fin_bar();
                 own_ready = s_last != 0;
@@ -768,19 +859,25 @@ __global__ void __launch_bounds__(WsCfg<K, DC, RIDER>::T, 1) fp_ws_kernel(const 
                     sum_slabs(u, slab, nsplit);     // the hand-over buffer is ours until it is released below
                     fin_bar();
                 }
-            } else {
-                fin_bar();
             }
-            const bool rider_last = RIDER && (s_rlast != 0);
+#ifdef WS_DBG_BAR
+            fin_bar();
+#endif
             auto from_u = [&](int k, int d) { return u[k * D + d]; };
             if (own_ready) stage1(from_u);
+#ifndef WS_OLD_TICKET
+            if (RIDER && ftid == NFT - 32) s_rlast = ticket_thread && (ticket == ds_[kWRiderNsplit] - 1);
+#endif
             fin_bar();
+            const bool rider_last = RIDER && (s_rlast != 0);
             if constexpr (RIDER) {
                 if (rider_last) {
                     // last contributor of the protein's global fingerprint: finish this item's own domain, then add
                     // the rider slabs in slot order into the (still owned) hand-over buffer and finish the global one
                     if (own_ready) finish_rest(dom, layer);
+#ifdef WS_OLD_TICKET
                     if (ftid == 0) s_flag = 0;
+#endif
                     __threadfence();
                     sum_slabs(u, p.partials + (int64_t)ds_[kWRiderSlabBase] * (K * D), ds_[kWRiderNsplit]);
                     fin_bar();
