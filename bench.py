@@ -8,8 +8,9 @@ Primary line = BASELINE.json metric part (i), domain fingerprints/s, on configs[
   100k synthetic domains, L ~ U{40..500}, two ESM-2 layers x 1280 fp32.  A step is one batch of
   --batch domains (default 4096, ~11 GB of embeddings: far larger than the 126 MB L2); the
   default 200 steps stream 819,200 domains (8x the 100k of configs[1], ~0.4 s timed).  `value` times the kernel path with inputs resident in
-  HBM; `e2e` times the public Python API (`quantize_batch` on Fingerprint objects) with pinned host
-  embeddings, H2D + kernel + D2H inside the timed region.
+  HBM; `e2e` times the public Python API (`quantize_stream`: `quantize_batch` on lists of Fingerprint objects, three
+  batches in flight) with pinned host embeddings, H2D + kernel + D2H of every batch inside the timed region
+  (`e2e.single_call`: the same batches through back-to-back `quantize_batch` calls).
 The same JSON line carries part (ii) of the metric, L1 top-50 query.DB pairs/s, with the database sharded over the
 N ranks (contiguous ranges, NCCL exchange of packed keys, merge by (distance, position)):
   `search`          configs[4]: 10k-query batch x 50M fingerprints (24 GB)
@@ -225,7 +226,7 @@ def run_ours(args):
     import torch.distributed as dist
     from dctdomain_b200 import _lib
     from dctdomain_b200 import index as dindex
-    from dctdomain_b200.fingerprint import Fingerprint, execute_plan, make_plan, quantize_batch
+    from dctdomain_b200.fingerprint import Fingerprint, execute_plan, make_plan, quantize_batch, quantize_stream
     from dctdomain_b200.sharded import ShardedIndex, shard_bounds
     import synth
 
@@ -346,32 +347,51 @@ def run_ours(args):
         link_all = {'per_rank_max': float(t[0].item()), 'per_rank_min': float(-t[1].item()), 'aggregate': float(tsum.item())}
     del big, dbig
 
-    def e2e_run(staging):
-        def one():
-            fps = [Fingerprint(pid=pid, seq='', embed=emb, domains=[f'1-{Ln}'], quants={}) for pid, Ln, emb in host_fps]
-            quantize_batch(fps, QDIM, device=dev, staging=staging)
-        for _ in range(2):
-            one()
+    def make_batch():
+        return [Fingerprint(pid=pid, seq='', embed=emb, domains=[f'1-{Ln}'], quants={}) for pid, Ln, emb in host_fps]
+
+    def e2e_run(staging, steps, pipelined):
+        """steps batches of Be proteins through the public API; every batch: Fingerprint objects, H2D of all embeddings,
+        kernel, D2H, quants dicts.  pipelined: quantize_stream (three batches in flight), else one quantize_batch call
+        after the other."""
+        def run(n):
+            if pipelined:
+                for _ in quantize_stream((make_batch() for _ in range(n)), QDIM, device=dev, depth=3, staging=staging):
+                    pass
+            else:
+                for _ in range(n):
+                    quantize_batch(make_batch(), QDIM, device=dev, staging=staging)
+        run(3)
         barrier()
         t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            one()
+        run(steps)
         barrier()
         return max_over_ranks(time.perf_counter() - t0)
 
-    e2e_steps = max(3, min(args.steps, 8))
-    e2e_s = e2e_run('auto')
+    e2e_steps = max(3, min(args.steps, 16))
+    e2e_s = e2e_run('auto', e2e_steps, True)
+    single_s = e2e_run('auto', max(3, e2e_steps // 2), False)
     e2e = {'value': Be * e2e_steps * world / e2e_s, 'unit': 'fingerprints/s', 'h2d_bytes_per_step': h2d,
            'd2h_bytes_per_step': d2h, 'steps': e2e_steps, 'domains_per_step': Be,
            'h2d_GBps_achieved': h2d * e2e_steps / e2e_s / 1e9, 'h2d_GBps_link_pinned_copy': link_gbps,
            'h2d_GBps_link_all_ranks_copying': link_all,
-           'api': 'dctdomain_b200.fingerprint.quantize_batch(list[Fingerprint]) with pinned host embeddings'}
+           'h2d_GBps_ceiling_sm_reads': 51.5,
+           'single_call': {'value': Be * max(3, e2e_steps // 2) * world / single_s, 'unit': 'fingerprints/s',
+                           'api': 'one quantize_batch(list[Fingerprint]) call after the other (no overlap between calls)'},
+           'api': 'dctdomain_b200.fingerprint.quantize_stream(batches of list[Fingerprint]) with pinned host embeddings: '
+                  'quantize_batch per batch, three batches in flight (H2D of one overlaps the host work of its neighbours); '
+                  'every byte of every batch crosses PCIe inside the timed region',
+           'note': 'h2d ceiling: SM-initiated reads of pinned memory (16-byte loads or TMA bulk copies alike) stop at 51.5 GB/s on '
+                   'this link, one copy-engine transfer at 55.6, one transfer per array at 47.6 (scripts/microbench/h2d_pull.cu, '
+                   'scripts/e2e_ab.py)'}
     if world > 1:
         # the same through one copy-engine transfer per array instead of the gather kernel: which staging route shares
         # the host's memory and PCIe root complexes better when every rank is copying
-        dma_s = e2e_run('dma')
-        e2e['staging_gather_vs_dma'] = {'gather_fingerprints_per_s': e2e['value'], 'dma_fingerprints_per_s': Be * e2e_steps * world / dma_s,
-                                        'per_rank_GBps_gather': h2d * e2e_steps / e2e_s / 1e9, 'per_rank_GBps_dma': h2d * e2e_steps / dma_s / 1e9}
+        dma_s = e2e_run('dma', max(3, e2e_steps // 2), True)
+        e2e['staging_gather_vs_dma'] = {'gather_fingerprints_per_s': e2e['value'],
+                                        'dma_fingerprints_per_s': Be * max(3, e2e_steps // 2) * world / dma_s,
+                                        'per_rank_GBps_gather': h2d * e2e_steps / e2e_s / 1e9,
+                                        'per_rank_GBps_dma': h2d * max(3, e2e_steps // 2) / dma_s / 1e9}
 
     # ---- e2e with device-resident embeddings (the ESM-2 output never leaves the GPU) ----
     e2e_device = None

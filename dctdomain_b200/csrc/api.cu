@@ -46,18 +46,18 @@ int dctd_h2d_rows(const void *const *h_src, const int64_t *nbytes, int64_t n, vo
  * array leaves a gap of a few microseconds between arrays).  d_table: n descriptors in device-accessible memory
  * (pinned host memory or device memory), every src / dst / nbytes a multiple of 16. */
 namespace {
-__global__ void __launch_bounds__(256) gather_kernel(const dctd_copy_desc *__restrict__ table, long long n) {
+__global__ void __launch_bounds__(128, 16) gather_kernel(const dctd_copy_desc *__restrict__ table, long long n) {
     for (long long e = blockIdx.x; e < n; e += gridDim.x) {
         const dctd_copy_desc dsc = table[e];
         const uint4 *src = reinterpret_cast<const uint4 *>(dsc.src);
         uint4 *dst = reinterpret_cast<uint4 *>(dsc.dst);
-        const long long m = dsc.nbytes / 16;
-        constexpr int U = 8;
-        for (long long i0 = threadIdx.x; i0 < m; i0 += (long long)blockDim.x * U) {
+        const unsigned int m = (unsigned int)(dsc.nbytes / 16);        // pieces are far below 64 GB
+        constexpr int U = 4;       // 64 bytes in flight per thread: with one CTA per SM still 1.2 MB, the link needs ~1 MB
+        for (unsigned int i0 = threadIdx.x; i0 < m; i0 += blockDim.x * U) {
             uint4 v[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                const long long i = i0 + (long long)u * blockDim.x;
+                const unsigned int i = i0 + u * blockDim.x;
                 if (i < m)
                     asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
                                  : "=r"(v[u].x), "=r"(v[u].y), "=r"(v[u].z), "=r"(v[u].w)
@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(256) gather_kernel(const dctd_copy_desc *__res
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                const long long i = i0 + (long long)u * blockDim.x;
+                const unsigned int i = i0 + u * blockDim.x;
                 if (i < m) dst[i] = v[u];
             }
         }
@@ -76,11 +76,25 @@ __global__ void __launch_bounds__(256) gather_kernel(const dctd_copy_desc *__res
 int dctd_h2d_gather(const dctd_copy_desc *d_table, int64_t n, void *stream) {
     if (n < 0 || (n > 0 && !d_table)) return DCTD_ERR_ARG;
     if (n == 0) return DCTD_OK;
+    // The link is saturated by ~1 MB in flight (measured: 32 CTAs x 256 threads x 128 bytes reach the 51.4 GB/s that
+    // 1184 CTAs reach; scripts/microbench/h2d_pull.cu), so the gather stays small enough to run NEXT TO the fingerprint
+    // kernel's one CTA per SM (608 threads x 96 registers, 223 KB of shared memory): one CTA of 128 threads per SM, no
+    // shared memory, and <= 32 registers - the register file is split over the four SM sub-partitions, the fingerprint
+    // kernel's 19 warps leave 1024 registers in three of them, i.e. room for one warp of 32 registers each (with 48
+    // registers the big kernel never got onto an SM before the whole gather launch had ended:
+    // scripts/microbench/coreside.cu).  In quantize_stream the copies of batch i+1 then run beside the fingerprint
+    // kernel of batch i instead of keeping it off the SMs.
     int dev = 0, n_sm = 0;
     DCTD_CUDA_TRY(cudaGetDevice(&dev));
     DCTD_CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-    const int grid = (int)(n < (int64_t)n_sm * 8 ? n : (int64_t)n_sm * 8);
-    gather_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_table, (long long)n);
+    const int grid = (int)(n < (int64_t)n_sm ? n : (int64_t)n_sm);
+    // An SM changes its L1 / shared-memory split only when it is idle.  The fingerprint kernel needs the maximum shared
+    // carveout; asking for the same split here (the loads bypass L1 anyway) lets its CTAs start on SMs that run gather
+    // CTAs (same microbenchmark: with the default carveout the big kernel waits for the end of the gather launch, 30 ms;
+    // with this attribute it is done 1.7 ms after the gather began).
+    DCTD_CUDA_TRY(cudaFuncSetAttribute(gather_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                       (int)cudaSharedmemCarveoutMaxShared));
+    gather_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(d_table, (long long)n);
     DCTD_LAUNCH_CHECK();
     return DCTD_OK;
 }

@@ -394,7 +394,7 @@ def _retire(device, plan):
 
 
 def quantize_batch(fps, qdim=(3, 80, 3, 80), device=None, maxlen=DEFAULT_MAXLEN, overlap=OVERLAP, plan_flags: int = 0,
-                   quants_dtype=np.int64, staging: str = 'auto', _timing=None):
+                   quants_dtype=np.int64, staging: str = 'auto', _timing=None, _copy_stream=None, _turn=None):
     """``quantize`` for a list of Fingerprint-like objects in one kernel launch per (n, m) group.
 
     Each object needs ``embed`` ({layer: [L, D] array | list of window arrays}), ``domains`` (list of
@@ -436,7 +436,9 @@ def quantize_batch(fps, qdim=(3, 80, 3, 80), device=None, maxlen=DEFAULT_MAXLEN,
         stream = main_stream.cuda_stream
         # host arrays arrive as many separate allocations; they are staged on a side stream (batched submission,
         # dctd_h2d_rows) while this thread keeps walking the batch, the compute stream joins before the kernel
-        aux_stream = _aux_stream(dev)
+        # (quantize_stream hands in one copy stream for all batches in flight and a turn: batches queue their copies one
+        # after the other, so the link finishes batch i before it starts on batch i + 1 instead of sharing itself out)
+        aux_stream = _copy_stream if _copy_stream is not None else _aux_stream(dev)
         aux_stream.wait_stream(main_stream)
         have = _stage.get(_owner(dev))    # staging buffer of an earlier call (kept alive until this call returns)
         state = {'done': 0, 'bases': [], 'tab': 0}  # bases: [(first h index, device address that h_off is relative to)]
@@ -448,6 +450,10 @@ def quantize_batch(fps, qdim=(3, 80, 3, 80), device=None, maxlen=DEFAULT_MAXLEN,
             lo = state['done']
             if lo == len(h_addr):
                 return
+            if _turn is not None and not _turn[0].is_now(_turn[1]):
+                if not final:
+                    return              # not this batch's turn yet: keep walking, the copies are issued later
+                _turn[0].wait(_turn[1])
             if have is not None and stage_bytes <= have.numel():
                 base = have.data_ptr()
                 if not state['bases']:
@@ -458,6 +464,10 @@ def quantize_batch(fps, qdim=(3, 80, 3, 80), device=None, maxlen=DEFAULT_MAXLEN,
                 state['bases'].append((lo, base))
             else:
                 return
+            if _timing is not None and 'copies_begin_event' not in _timing:
+                ev0 = torch.cuda.Event(enable_timing=True)
+                ev0.record(aux_stream)
+                _timing['copies_begin_event'] = ev0
             a_src = np.array(h_addr[lo:], dtype=np.uint64)
             a_len = np.array(h_bytes[lo:], dtype=np.int64)
             a_off = np.array(h_off[lo:], dtype=np.int64)
@@ -533,6 +543,9 @@ def quantize_batch(fps, qdim=(3, 80, 3, 80), device=None, maxlen=DEFAULT_MAXLEN,
 
         flush(final=True)
         main_stream.wait_stream(aux_stream)
+        if _turn is not None:
+            _turn[0].wait(_turn[1])
+            _turn[0].done(_turn[1])     # every copy of this batch is queued: the next batch may queue its own
         if h_addr:
             def resolve(hi):
                 base = state['bases'][-1][1] if hi >= state['bases'][-1][0] else state['bases'][0][1]
@@ -543,7 +556,7 @@ def quantize_batch(fps, qdim=(3, 80, 3, 80), device=None, maxlen=DEFAULT_MAXLEN,
     if _timing is not None:                 # debug hook (scripts/e2e_phases.py): host time stamps of the call's phases
         import time as _t
         _timing['walk_done'] = _t.perf_counter()
-        ev = torch.cuda.Event()
+        ev = torch.cuda.Event(enable_timing=True)
         ev.record(main_stream)
         _timing['copies_event'] = ev
 
@@ -572,8 +585,16 @@ def quantize_batch(fps, qdim=(3, 80, 3, 80), device=None, maxlen=DEFAULT_MAXLEN,
             outs.append((out, n * m, lids, plan))
         if _timing is not None:
             _timing['launched'] = _t.perf_counter()
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record(main_stream)
+            _timing['kernel_event'] = ev
             _timing['copies_event'].synchronize()
             _timing['copies_done'] = _t.perf_counter()
+        # wait on an event first: Event.synchronize releases the GIL, so the other batches of quantize_stream keep
+        # walking / assembling while this one is on the device (the blocking copy below then returns at once)
+        done = torch.cuda.Event()
+        done.record(main_stream)
+        done.synchronize()
         for out, nm, lids, _plan in outs:
             arr = out.cpu().numpy()
             for pos, li in enumerate(lids):
@@ -607,6 +628,84 @@ def quantize_batch(fps, qdim=(3, 80, 3, 80), device=None, maxlen=DEFAULT_MAXLEN,
         torch.cuda.current_stream(dev).synchronize()   # staged copies still read the host arrays
     del keep
     return fps
+
+
+_stream_pool = None          # worker threads of quantize_stream (persistent: their scratch caches are reused)
+_stream_local = None         # threading.local: one CUDA stream per worker thread and device
+_copy_streams: dict = {}     # device -> the copy stream the batches of quantize_stream share
+
+
+class _Turn:
+    """Batches of one quantize_stream call queue their host-to-device copies in submission order."""
+
+    def __init__(self):
+        import threading
+        self.cond = threading.Condition()
+        self.now = 0
+
+    def is_now(self, seq):
+        return self.now == seq
+
+    def wait(self, seq):
+        with self.cond:
+            while self.now < seq:
+                self.cond.wait()
+
+    def done(self, seq):
+        with self.cond:
+            if self.now == seq:
+                self.now = seq + 1
+                self.cond.notify_all()
+
+
+def quantize_stream(batches, qdim=(3, 80, 3, 80), device=None, depth: int = 2, **kwargs):
+    """``quantize_batch`` over an iterable of batches with ``depth`` batches in flight: the loop of ``make_db.main``
+    (src/make_db.py:36-51: embed a batch, fingerprint it, store it) as a generator that yields the finished batches in
+    order.  While the host arrays of one batch cross PCIe, the next batch is walked and planned and the previous one is
+    turned into ``quants`` dicts, so the link never waits for the interpreter (a single ``quantize_batch`` call leaves it
+    idle for ~2 ms of 30 per 512 proteins).  Every batch runs as one ordinary ``quantize_batch`` call on a worker thread
+    with its own CUDA stream; the scratch caches are per (device, stream, thread) and the worker threads are kept, so the
+    calls share nothing but the copy stream, on which the batches queue their copies one after the other (copies of two
+    batches sharing the link would finish together and leave the same gap).  Results are the bytes ``quantize_batch``
+    gives.  ``kwargs`` go to ``quantize_batch``; an exception of a batch is raised when that batch is due."""
+    import collections
+    import threading
+    from concurrent.futures import ThreadPoolExecutor
+    global _stream_pool, _stream_local
+    if not 1 <= depth <= 4:
+        raise ValueError('depth must be 1..4')
+    dev = _device(device)
+    if _stream_pool is None:
+        _stream_local = threading.local()
+        _stream_pool = ThreadPoolExecutor(max_workers=4, thread_name_prefix='dctd-fp')
+    copy_stream = _copy_streams.get(dev)
+    if copy_stream is None:
+        copy_stream = _copy_streams[dev] = torch.cuda.Stream(device=dev)
+    turn = _Turn()
+
+    def work(fps, seq):
+        streams = getattr(_stream_local, 'by_device', None)
+        if streams is None:
+            streams = _stream_local.by_device = {}
+        st = streams.get(dev)
+        if st is None:
+            # high priority: when the copies of the next batch (gather kernels on the default-priority copy stream)
+            # fill the SMs, this batch's fingerprint kernel gets the next free slots instead of waiting for them to end
+            st = streams[dev] = torch.cuda.Stream(device=dev, priority=-1)
+        try:
+            with torch.cuda.device(dev), torch.cuda.stream(st):
+                return quantize_batch(fps, qdim, device=dev, _copy_stream=copy_stream, _turn=(turn, seq), **kwargs)
+        finally:
+            turn.wait(seq)          # a batch that raised, was empty or needed no copies still passes the turn on
+            turn.done(seq)
+
+    pending = collections.deque()
+    for seq, fps in enumerate(batches):
+        pending.append(_stream_pool.submit(work, fps, seq))
+        if len(pending) >= depth:
+            yield pending.popleft().result()
+    while pending:
+        yield pending.popleft().result()
 
 
 @dataclass

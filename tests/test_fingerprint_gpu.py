@@ -144,6 +144,42 @@ def test_pinned_host_arrays_take_the_gather_path_and_match():
                 assert np.array_equal(a.quants[d], b.quants[d]), (kind, a.pid, d)
 
 
+def test_quantize_stream_overlaps_batches_and_gives_the_same_bytes():
+    """quantize_stream (batches in flight on worker threads, one CUDA stream each) yields the batches in order with the
+    bytes quantize_batch gives; an exception of a batch surfaces when that batch is due."""
+    from dctdomain_b200.fingerprint import Fingerprint, quantize_batch, quantize_stream
+
+    def batch(seed, pin):
+        fps = []
+        for i, c in enumerate(cases.FP_CASES[:6]):
+            emb = synth.layers(c['seed'] + 100 * seed, c['L'], c['D'], c['kind'])
+            if pin:
+                emb = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for k, v in emb.items()}
+            fps.append(Fingerprint(pid=f'{seed}/{c["name"]}', seq='A' * c['L'], embed=emb, domains=list(c['domains']), quants={}))
+        return fps
+
+    same_d = [c['D'] for c in cases.FP_CASES[:6]]
+    if len(set(same_d)) != 1:
+        pytest.skip('the first cases no longer share D')
+    want = [quantize_batch(batch(s, s % 2 == 0), [3, 80, 3, 80]) for s in range(7)]
+    for depth in (1, 2, 3):
+        got = list(quantize_stream((batch(s, s % 2 == 0) for s in range(7)), [3, 80, 3, 80], depth=depth))
+        assert len(got) == 7
+        for wb, gb in zip(want, got):
+            assert [f.pid for f in wb] == [f.pid for f in gb]
+            for a, b in zip(wb, gb):
+                assert a.domains == b.domains
+                for d in a.domains:
+                    assert np.array_equal(a.quants[d], b.quants[d]), (depth, a.pid, d)
+    assert list(quantize_stream([], [3, 80, 3, 80])) == []
+    bad = batch(0, False)
+    bad[1].embed = {15: bad[1].embed[15]}          # one layer missing: quantize_batch raises ValueError
+    it = quantize_stream([batch(1, False), bad, batch(2, False)], [3, 80, 3, 80], depth=2)
+    assert [f.pid for f in next(it)] == [f.pid for f in want[1]]
+    with pytest.raises(ValueError):
+        next(it)
+
+
 def test_properties_at_full_size():
     """Size-independent properties on a batch of configs[1]-sized domains: each 80-byte row holds exactly
     the values 0 and 127 (min-max), the result is invariant to a per-column offset and a positive scale of

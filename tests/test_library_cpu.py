@@ -377,3 +377,12 @@ def test_batch_domain_parser_matches_the_line_by_line_mirror(lib):
         parse_domains_batch([['1-5-7']], [10])           # the reference's split('-') fails the same way
     with pytest.raises(ValueError):
         parse_domains_batch([['a-5']], [10])
+
+
+def test_hostbind_cpulist_parser_and_noop_without_topology():
+    """hostbind: the sysfs cpulist syntax, and binding is a no-op that reports itself when the platform exposes no
+    NUMA node for the device (the pool's boxes are single-node VMs)."""
+    from dctdomain_b200 import hostbind
+    assert hostbind._parse_cpulist('0-3,8,10-11\n') == {0, 1, 2, 3, 8, 10, 11}
+    assert hostbind._parse_cpulist('') == set()
+    assert hostbind._parse_cpulist('5') == {5}
