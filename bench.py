@@ -350,36 +350,76 @@ def run_ours(args):
     def make_batch():
         return [Fingerprint(pid=pid, seq='', embed=emb, domains=[f'1-{Ln}'], quants={}) for pid, Ln, emb in host_fps]
 
+    store = dist.distributed_c10d._get_default_store() if world > 1 else None
+    e2e_runs = [0]
+
     def e2e_run(staging, steps, pipelined):
-        """steps batches of Be proteins through the public API; every batch: Fingerprint objects, H2D of all embeddings,
-        kernel, D2H, quants dicts.  pipelined: quantize_stream (three batches in flight), else one quantize_batch call
-        after the other."""
-        def run(n):
+        """steps * world batches of Be proteins through the public API; every batch: Fingerprint objects, H2D of all
+        embeddings, kernel, D2H, quants dicts.  pipelined: quantize_stream (three batches in flight), else one
+        quantize_batch call after the other.  With several ranks the batches are one shared pool: a rank draws the next
+        batch index from a counter in the rendezvous store when its pipeline has room (a work queue, what a make_db over
+        several GPUs would do) - the ranks of a box do not get the same share of the host's PCIe / memory bandwidth
+        (gpurun_out/r2g_numa_n8.log: 20.5 vs 35.7 GB/s per rank with all eight copying), and with equal shares the slow
+        ranks would set the time.  Returns (seconds: max over ranks, batches this rank processed)."""
+        e2e_runs[0] += 1
+        key = f'dctd_e2e_pool_{e2e_runs[0]}'
+        mine = [0]
+
+        def pool(total):
+            if store is None:
+                for _ in range(total):
+                    mine[0] += 1
+                    yield make_batch()
+            else:
+                while int(store.add(key, 1)) <= total:
+                    mine[0] += 1
+                    yield make_batch()
+
+        def run(batches):
             if pipelined:
-                for _ in quantize_stream((make_batch() for _ in range(n)), QDIM, device=dev, depth=3, staging=staging):
+                for _ in quantize_stream(batches, QDIM, device=dev, depth=e2e_depth, staging=staging):
                     pass
             else:
-                for _ in range(n):
-                    quantize_batch(make_batch(), QDIM, device=dev, staging=staging)
-        run(3)
+                for fps in batches:
+                    quantize_batch(fps, QDIM, device=dev, staging=staging)
+        run(make_batch() for _ in range(3))
         barrier()
         t0 = time.perf_counter()
-        run(steps)
+        run(pool(steps * world))
         barrier()
-        return max_over_ranks(time.perf_counter() - t0)
+        return max_over_ranks(time.perf_counter() - t0), mine[0]
 
-    e2e_steps = max(3, min(args.steps, 16))
-    e2e_s = e2e_run('auto', e2e_steps, True)
-    single_s = e2e_run('auto', max(3, e2e_steps // 2), False)
-    e2e = {'value': Be * e2e_steps * world / e2e_s, 'unit': 'fingerprints/s', 'h2d_bytes_per_step': h2d,
+    def sum_over_ranks(x):
+        if world == 1:
+            return float(x)
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t)
+        return float(t.item())
+
+    e2e_steps = max(3, min(args.steps, 16)) * (2 if world > 1 else 1)     # a longer pool keeps the queue's tail (<= depth batches) small
+    e2e_depth = 3 if world == 1 else 2
+    half_steps = max(3, e2e_steps // 2)
+    e2e_s, n_mine = e2e_run('auto', e2e_steps, True)
+    bytes_all = sum_over_ranks(n_mine * h2d)                       # bytes that crossed PCIe on all ranks together
+    counts = None
+    if world > 1:
+        t = torch.zeros(world, dtype=torch.float64, device=dev)
+        t[rank] = n_mine
+        dist.all_reduce(t)
+        counts = [int(v) for v in t.tolist()]
+    single_s, _ = e2e_run('auto', half_steps, False)
+    e2e = {'value': Be * e2e_steps * world / e2e_s, 'unit': 'fingerprints/s', 'h2d_bytes_per_step': int(bytes_all / (e2e_steps * world)),
            'd2h_bytes_per_step': d2h, 'steps': e2e_steps, 'domains_per_step': Be,
-           'h2d_GBps_achieved': h2d * e2e_steps / e2e_s / 1e9, 'h2d_GBps_link_pinned_copy': link_gbps,
+           'h2d_GBps_achieved': bytes_all / world / e2e_s / 1e9, 'h2d_GBps_link_pinned_copy': link_gbps,
            'h2d_GBps_link_all_ranks_copying': link_all,
            'h2d_GBps_ceiling_sm_reads': 51.5,
-           'single_call': {'value': Be * max(3, e2e_steps // 2) * world / single_s, 'unit': 'fingerprints/s',
+           'batches_per_rank': counts,
+           'distribution': 'one rank' if world == 1 else 'work queue: ranks draw batches of 512 proteins from a shared counter '
+                           '(steps x ranks batches in all); h2d_GBps_achieved is the mean over ranks',
+           'single_call': {'value': Be * half_steps * world / single_s, 'unit': 'fingerprints/s',
                            'api': 'one quantize_batch(list[Fingerprint]) call after the other (no overlap between calls)'},
            'api': 'dctdomain_b200.fingerprint.quantize_stream(batches of list[Fingerprint]) with pinned host embeddings: '
-                  'quantize_batch per batch, three batches in flight (H2D of one overlaps the host work of its neighbours); '
+                  f'quantize_batch per batch, {e2e_depth} batches in flight (H2D of one overlaps the host work of its neighbours); '
                   'every byte of every batch crosses PCIe inside the timed region',
            'note': 'h2d ceiling: SM-initiated reads of pinned memory (16-byte loads or TMA bulk copies alike) stop at 51.5 GB/s on '
                    'this link, one copy-engine transfer at 55.6, one transfer per array at 47.6 (scripts/microbench/h2d_pull.cu, '
@@ -387,11 +427,9 @@ def run_ours(args):
     if world > 1:
         # the same through one copy-engine transfer per array instead of the gather kernel: which staging route shares
         # the host's memory and PCIe root complexes better when every rank is copying
-        dma_s = e2e_run('dma', max(3, e2e_steps // 2), True)
+        dma_s, _ = e2e_run('dma', half_steps, True)
         e2e['staging_gather_vs_dma'] = {'gather_fingerprints_per_s': e2e['value'],
-                                        'dma_fingerprints_per_s': Be * max(3, e2e_steps // 2) * world / dma_s,
-                                        'per_rank_GBps_gather': h2d * e2e_steps / e2e_s / 1e9,
-                                        'per_rank_GBps_dma': h2d * max(3, e2e_steps // 2) / dma_s / 1e9}
+                                        'dma_fingerprints_per_s': Be * half_steps * world / dma_s}
 
     # ---- e2e with device-resident embeddings (the ESM-2 output never leaves the GPU) ----
     e2e_device = None
