@@ -1,6 +1,6 @@
 #!/bin/bash
 # GPU box: round-2 captures.  Every ncu run follows a plain run of the same command that exited 0.
-# usage: scripts/profile_r2.sh <tag>
+# usage: scripts/profile_r2.sh <tag>      (FP_ONLY=1: only the launch list and the two fingerprint-kernel captures)
 set -u
 TAG=${1:-r2}
 mkdir -p gpurun_out
@@ -16,6 +16,7 @@ python scripts/fp_protein.py 2048 4 > gpurun_out/prof_plain_rider_$TAG.log 2>&1 
 ncu --set full --clock-control none --import-source on -k regex:fp_ws_kernel -s 2 -c 1 \
     -o gpurun_out/fprider_$TAG -f python scripts/fp_protein.py 2048 4 > gpurun_out/ncu_fprider_$TAG.log 2>&1
 echo "rider capture rc=$?"
+if [ -z "${FP_ONLY:-}" ]; then
 python scripts/l1_phases.py stream,ref13 > gpurun_out/prof_plain_stream_$TAG.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:l1_stream_fused -s 1 -c 1 \
     -o gpurun_out/l1stream_$TAG -f python scripts/l1_phases.py stream > gpurun_out/ncu_l1stream_$TAG.log 2>&1
@@ -27,6 +28,7 @@ python scripts/dctsim_run.py 4000 > gpurun_out/prof_plain_dctsim_$TAG.log 2>&1 &
 ncu --set full --clock-control none --import-source on -k regex:l1_protein_kernel -s 1 -c 1 \
     -o gpurun_out/l1prot_$TAG -f python scripts/dctsim_run.py 4000 > gpurun_out/ncu_l1prot_$TAG.log 2>&1
 echo "protein capture rc=$?"
+fi
 # summaries are made here: the reports together exceed what gpurun copies back (64 MiB)
 for pair in "fp:fp_ws_kernelILi2ELi1280ELb0:fingerprint" "fprider:fp_ws_kernelILi2ELi1280ELb1:fingerprint" \
             "l1stream:l1_stream_fused_kernel:l1topk" "l1prot:l1_protein_kernel:l1topk"; do
@@ -37,5 +39,5 @@ for pair in "fp:fp_ws_kernelILi2ELi1280ELb0:fingerprint" "fprider:fp_ws_kernelIL
   python scripts/ncu_lines.py $rep "$pat" $obj 70 > gpurun_out/${name}_${TAG}_lines.txt 2>&1
   rm -f $rep
 done
-cat gpurun_out/prof_plain_stream_$TAG.log gpurun_out/prof_plain_dctsim_$TAG.log | tail -12
+cat gpurun_out/prof_plain_stream_$TAG.log gpurun_out/prof_plain_dctsim_$TAG.log 2>/dev/null | tail -12
 ls -la gpurun_out | tail -20
