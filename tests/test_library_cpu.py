@@ -386,3 +386,32 @@ def test_hostbind_cpulist_parser_and_noop_without_topology():
     assert hostbind._parse_cpulist('0-3,8,10-11\n') == {0, 1, 2, 3, 8, 10, 11}
     assert hostbind._parse_cpulist('') == set()
     assert hostbind._parse_cpulist('5') == {5}
+
+
+def test_stream_turns_are_taken_in_submission_order():
+    """quantize_stream's _Turn: batches queue their copies strictly in submission order, whatever order the worker
+    threads reach the point in; done() of a batch that is not at turn is a no-op, wait() of a passed turn returns."""
+    import random
+    import threading
+    import time
+    from dctdomain_b200.fingerprint import _Turn
+    turn, order, lock = _Turn(), [], threading.Lock()
+
+    def worker(seq, delay):
+        time.sleep(delay)
+        assert turn.is_now(seq) == (turn.now == seq)
+        turn.wait(seq)
+        with lock:
+            order.append(seq)
+        turn.done(seq)
+        turn.done(seq)                 # second call: the turn has moved on, nothing happens
+        turn.wait(seq)                 # a passed turn does not block
+
+    rnd = random.Random(3)
+    threads = [threading.Thread(target=worker, args=(s, rnd.random() * 0.05)) for s in range(12)]
+    for t in reversed(threads):
+        t.start()
+    for t in threads:
+        t.join(timeout=10)
+        assert not t.is_alive()
+    assert order == list(range(12)) and turn.now == 12
