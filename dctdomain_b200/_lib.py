@@ -63,6 +63,7 @@ def lib():
         'dctd_launch_count': (i64, [C.c_int]),
         'dctd_h2d_rows': (C.c_int, [vp, vp, i64, vp, vp, vp]),
         'dctd_h2d_gather': (C.c_int, [vp, i64, vp]),
+        'dctd_h2d_rows_staged': (C.c_int, [vp, vp, i64, vp, vp, vp, i64, C.c_int32, C.c_int32, vp]),
         'dctd_parse_domains': (C.c_int, [vp, i64, i32, vp, vp, i32, vp, vp, vp, vp, i64, C.POINTER(i32), C.POINTER(i32)]),
         'dctd_fp_plan_create': (C.c_int, [C.POINTER(FpGeometry), C.POINTER(vp)]),
         'dctd_fp_plan_create_ex': (C.c_int, [C.POINTER(FpGeometry), u32, C.POINTER(vp)]),

@@ -1,6 +1,12 @@
 // libdctd: version / error plumbing of the C ABI (include/dctd.h).
 #include "dctd_internal.cuh"
 
+#include <algorithm>
+#include <atomic>
+#include <cstring>
+#include <thread>
+#include <vector>
+
 namespace dctd {
 static thread_local cudaError_t g_last_cuda = cudaSuccess;
 static thread_local int64_t g_launches = 0;
@@ -37,6 +43,91 @@ int dctd_h2d_rows(const void *const *h_src, const int64_t *nbytes, int64_t n, vo
         if (nbytes[i] == 0) continue;
         DCTD_CUDA_TRY(cudaMemcpyAsync((char *)d_base + d_off[i], h_src[i], (size_t)nbytes[i], cudaMemcpyHostToDevice,
                                       (cudaStream_t)stream));
+    }
+    return DCTD_OK;
+}
+
+/* Pageable host arrays: n_threads host threads copy slot-sized chunks of the destination range into a pinned ring, one
+ * copy-engine transfer per filled slot (see dctd.h).  Chunks are handed out in ascending order; chunk c uses slot
+ * c % n_slots once the transfer of chunk c - n_slots has completed (slot generation counter + event), so a worker only
+ * ever waits for an EARLIER chunk, which some worker took before: no cycle. */
+int dctd_h2d_rows_staged(const void *const *h_src, const int64_t *nbytes, int64_t n, void *d_base, const int64_t *d_off,
+                         void *h_ring, int64_t slot_bytes, int32_t n_slots, int32_t n_threads, void *stream) {
+    if (n < 0 || slot_bytes <= 0 || n_slots < 2 || n_slots > 256 || n_threads < 1 || n_threads > 64) return DCTD_ERR_ARG;
+    if (n == 0) return DCTD_OK;
+    if (!h_src || !nbytes || !d_base || !d_off || !h_ring) return DCTD_ERR_ARG;
+    for (int64_t i = 0; i < n; ++i) {
+        if (nbytes[i] < 0 || (nbytes[i] > 0 && !h_src[i])) return DCTD_ERR_ARG;
+        if (i + 1 < n && d_off[i] + nbytes[i] > d_off[i + 1]) return DCTD_ERR_ARG;      // ascending, non-overlapping
+    }
+    const int64_t lo0 = d_off[0], hi0 = d_off[n - 1] + nbytes[n - 1];
+    const int64_t nchunks = (hi0 - lo0 + slot_bytes - 1) / slot_bytes;
+    if (nchunks <= 0) return DCTD_OK;
+    int dev = 0;
+    DCTD_CUDA_TRY(cudaGetDevice(&dev));
+    std::vector<cudaEvent_t> ev((size_t)n_slots, nullptr);
+    for (int s = 0; s < n_slots; ++s) {
+        const cudaError_t e = cudaEventCreateWithFlags(&ev[s], cudaEventDisableTiming);
+        if (e != cudaSuccess) {
+            for (int t = 0; t < s; ++t) (void)cudaEventDestroy(ev[t]);
+            dctd::set_cuda_error(e);
+            return DCTD_ERR_CUDA;
+        }
+    }
+    std::vector<std::atomic<int64_t>> gen((size_t)n_slots);
+    for (auto &g : gen) g.store(0, std::memory_order_relaxed);
+    std::atomic<int64_t> next{0};
+    std::atomic<int> failed{0};
+    char *const ring = static_cast<char *>(h_ring);
+    char *const dbase = static_cast<char *>(d_base);
+    const cudaStream_t st = (cudaStream_t)stream;
+    auto worker = [&]() {
+        if (cudaSetDevice(dev) != cudaSuccess) { failed.store((int)cudaGetLastError() | 0x10000); return; }
+        for (;;) {
+            const int64_t c = next.fetch_add(1, std::memory_order_relaxed);
+            if (c >= nchunks || failed.load(std::memory_order_relaxed)) return;
+            const int s = (int)(c % n_slots);
+            const int64_t g = c / n_slots;
+            while (gen[s].load(std::memory_order_acquire) != g) {
+                if (failed.load(std::memory_order_relaxed)) return;
+                std::this_thread::yield();
+            }
+            cudaError_t e = cudaSuccess;
+            if (g > 0) e = cudaEventSynchronize(ev[s]);        // the slot's previous transfer has read it
+            char *slot = ring + (size_t)s * slot_bytes;
+            const int64_t lo = lo0 + c * slot_bytes, hi = std::min(lo + slot_bytes, hi0);
+            if (e == cudaSuccess) {
+                int64_t i = std::upper_bound(d_off, d_off + n, lo) - d_off - 1;      // last destination starting at or before lo
+                if (i < 0) i = 0;
+                for (; i < n && d_off[i] < hi; ++i) {
+                    const int64_t a = std::max(lo, d_off[i]), b = std::min(hi, d_off[i] + nbytes[i]);
+                    if (b > a) memcpy(slot + (a - lo), static_cast<const char *>(h_src[i]) + (a - d_off[i]), (size_t)(b - a));
+                }
+                e = cudaMemcpyAsync(dbase + lo, slot, (size_t)(hi - lo), cudaMemcpyHostToDevice, st);
+            }
+            if (e == cudaSuccess) e = cudaEventRecord(ev[s], st);
+            if (e != cudaSuccess) failed.store((int)e | 0x10000);
+            gen[s].store(g + 1, std::memory_order_release);
+        }
+    };
+    const int nt = (int)std::min<int64_t>(n_threads, nchunks);
+    std::vector<std::thread> pool;
+    pool.reserve((size_t)std::max(0, nt - 1));
+    for (int t = 1; t < nt; ++t) pool.emplace_back(worker);
+    worker();
+    for (auto &t : pool) t.join();
+    cudaError_t e = cudaSuccess;
+    for (int s = 0; s < n_slots; ++s) {
+        if (gen[s].load() > 0 && e == cudaSuccess) e = cudaEventSynchronize(ev[s]);
+        (void)cudaEventDestroy(ev[s]);
+    }
+    if (failed.load()) {
+        dctd::set_cuda_error((cudaError_t)(failed.load() & 0xffff));
+        return DCTD_ERR_CUDA;
+    }
+    if (e != cudaSuccess) {
+        dctd::set_cuda_error(e);
+        return DCTD_ERR_CUDA;
     }
     return DCTD_OK;
 }

@@ -170,6 +170,33 @@ def _pinned_table(device, n_entries: int) -> np.ndarray:
     return t
 
 
+_RING_SLOT = 4 << 20           # bytes per slot of the pinned ring pageable arrays are staged through
+_RING_SLOTS = 16
+_rings: dict = {}
+
+
+def _pinned_ring(device) -> torch.Tensor:
+    key = _owner(device)
+    r = _rings.get(key)
+    if r is None:
+        r = _rings[key] = torch.empty(_RING_SLOT * _RING_SLOTS, dtype=torch.uint8).pin_memory()
+    return r
+
+
+def _stage_threads() -> int:
+    """Host threads that copy pageable arrays into the pinned ring: DCTD_STAGE_THREADS, else half the CPUs this process may
+    run on, shared between the ranks of the box (LOCAL_WORLD_SIZE), at most 8."""
+    env = os.environ.get('DCTD_STAGE_THREADS')
+    if env:
+        return max(1, min(64, int(env)))
+    try:
+        cpus = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cpus = os.cpu_count() or 2
+    ranks = max(1, int(os.environ.get('LOCAL_WORLD_SIZE', '1') or 1))
+    return max(1, min(8, cpus // (2 * ranks)))
+
+
 _stage: dict = {}
 _aux: dict = {}
 
@@ -404,8 +431,9 @@ def quantize_batch(fps, qdim=(3, 80, 3, 80), device=None, maxlen=DEFAULT_MAXLEN,
     ``plan_flags``: per-call options of the work decomposition (``_lib.FP_PLAN_NO_FUSION`` ...).  ``quants_dtype``: dtype
     of the arrays put into ``quants`` - int64 is what the reference produces (``np.array`` of Python ints,
     src/fingerprint.py:200); ``np.int8`` skips the widening (same values, an eighth of the bytes).  ``staging``: how
-    pinned host arrays reach the device - 'auto' / 'gather' (one gather kernel pulling all arrays over PCIe) or 'dma' (one
-    copy-engine transfer per array, what pageable arrays always take).  Returns the list.
+    host arrays reach the device - 'auto' / 'gather' (pinned arrays: one gather kernel pulling all arrays over PCIe;
+    pageable arrays: host threads copy them into a pinned ring, one copy-engine transfer per 4 MB slot) or 'dma' (one
+    cudaMemcpyAsync per array, whatever the memory).  Returns the list.
     """
     fps = list(fps)
     if not fps:
@@ -450,6 +478,8 @@ def quantize_batch(fps, qdim=(3, 80, 3, 80), device=None, maxlen=DEFAULT_MAXLEN,
             lo = state['done']
             if lo == len(h_addr):
                 return
+            if not final and staging != 'dma' and not all(h_pin[lo:]):
+                return                  # pageable arrays go in one staged call at the end (host threads per call)
             if _turn is not None and not _turn[0].is_now(_turn[1]):
                 if not final:
                     return              # not this batch's turn yet: keep walking, the copies are issued later
@@ -488,6 +518,13 @@ def quantize_batch(fps, qdim=(3, 80, 3, 80), device=None, maxlen=DEFAULT_MAXLEN,
                     state['tab'] = t0 + total
                     keep.append(table)
                     _lib.check(L.dctd_h2d_gather(table.data_ptr() + t0 * 24, total, aux_stream.cuda_stream), 'dctd_h2d_gather')
+                elif staging != 'dma':
+                    # pageable arrays (numpy: what the reference's .cpu().numpy() leaves): host threads copy them into a
+                    # pinned ring, one copy-engine transfer per slot (cudaMemcpyAsync from pageable memory: ~10 GB/s)
+                    ring = _pinned_ring(dev)
+                    _lib.check(L.dctd_h2d_rows_staged(a_src.ctypes.data, a_len.ctypes.data, len(a_src), base, a_off.ctypes.data,
+                                                      ring.data_ptr(), _RING_SLOT, ring.numel() // _RING_SLOT, _stage_threads(),
+                                                      aux_stream.cuda_stream), 'dctd_h2d_rows_staged')
                 else:
                     _lib.check(L.dctd_h2d_rows(a_src.ctypes.data, a_len.ctypes.data, len(a_src), base,
                                                a_off.ctypes.data, aux_stream.cuda_stream), 'dctd_h2d_rows')

@@ -59,6 +59,18 @@ typedef struct dctd_copy_desc {
 } dctd_copy_desc;
 int dctd_h2d_gather(const dctd_copy_desc *d_table, int64_t n, void *stream);
 
+/* The same staging for PAGEABLE host arrays (what the reference's `.cpu().numpy()` leaves in Fingerprint.embed,
+ * src/embedding.py:191): cudaMemcpyAsync from pageable memory goes through the driver's own bounce buffer on one thread
+ * (~10 GB/s measured here).  This call copies with `n_threads` host threads into a caller-owned PINNED ring of `n_slots`
+ * slots of `slot_bytes` and issues one copy-engine transfer per filled slot.  The destinations must be ascending and
+ * non-overlapping (d_off[i] + nbytes[i] <= d_off[i+1]); the range d_off[0] .. d_off[n-1] + nbytes[n-1] is moved in
+ * slot-sized chunks, so small arrays share a transfer (bytes in the gaps between destinations are overwritten with
+ * unspecified values).  Returns after the last transfer has COMPLETED: the host arrays and the ring are free again;
+ * the data is visible to work queued on `stream` afterwards. */
+int dctd_h2d_rows_staged(const void *const *h_src, const int64_t *nbytes, int64_t n, void *d_base,
+                         const int64_t *d_off, void *h_ring, int64_t slot_bytes, int32_t n_slots, int32_t n_threads,
+                         void *stream);
+
 /* =====================================================================================
  * Hot path 1: DCT fingerprints ("quant2D")
  *   replaces reference src/fingerprint.py:110-201 (scale / idct_quant / get_doms / quantize)

@@ -180,6 +180,35 @@ def test_quantize_stream_overlaps_batches_and_gives_the_same_bytes():
         next(it)
 
 
+def test_h2d_rows_staged_moves_pageable_arrays_bit_exactly():
+    """dctd_h2d_rows_staged (host threads -> pinned ring -> one transfer per slot): arrays smaller and larger than a slot,
+    empty ones, gaps between the destinations; every destination holds its source afterwards, with 1 and 5 threads."""
+    import ctypes as C
+    from dctdomain_b200 import _lib
+    L = _lib.lib()
+    rs = np.random.RandomState(11)
+    sizes = [0, 16, 100, 4096, 70_000, 1 << 20, (1 << 20) + 17, 3_500_000, 5, 0, 900_001]
+    srcs = [rs.randint(0, 256, size=n).astype(np.uint8) for n in sizes]
+    off, pos = [], 64
+    for n in sizes:
+        off.append(pos)
+        pos += (n + 255) // 256 * 256 + (256 if n % 3 == 0 else 0)
+    dst = torch.zeros(pos + 64, dtype=torch.uint8, device='cuda')
+    ptrs = np.array([a.ctypes.data for a in srcs], dtype=np.uint64)
+    lens = np.array(sizes, dtype=np.int64)
+    offs = np.array(off, dtype=np.int64)
+    for slot, slots, threads in ((1 << 20, 3, 5), (64 << 10, 2, 1), (4 << 20, 16, 4)):
+        ring = torch.empty(slot * slots, dtype=torch.uint8).pin_memory()
+        dst.zero_()
+        st = torch.cuda.current_stream().cuda_stream
+        _lib.check(L.dctd_h2d_rows_staged(ptrs.ctypes.data, lens.ctypes.data, len(sizes), dst.data_ptr(), offs.ctypes.data,
+                                          ring.data_ptr(), slot, slots, threads, st), 'dctd_h2d_rows_staged')
+        got = dst.cpu().numpy()
+        for a, o in zip(srcs, off):
+            assert np.array_equal(got[o:o + len(a)], a), (slot, threads, len(a))
+        assert not got[:64].any() and not got[pos:].any()          # nothing outside the destination range is touched
+
+
 def test_properties_at_full_size():
     """Size-independent properties on a batch of configs[1]-sized domains: each 80-byte row holds exactly
     the values 0 and 127 (min-max), the result is invariant to a per-column offset and a positive scale of

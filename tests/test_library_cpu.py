@@ -415,3 +415,26 @@ def test_stream_turns_are_taken_in_submission_order():
         t.join(timeout=10)
         assert not t.is_alive()
     assert order == list(range(12)) and turn.now == 12
+
+
+def test_h2d_rows_staged_rejects_bad_arguments_without_a_device():
+    """dctd_h2d_rows_staged validates before it touches CUDA: overlapping / descending destinations, bad ring geometry."""
+    import ctypes as C
+    from dctdomain_b200 import _lib
+    L = _lib.lib()
+    src = np.zeros(64, dtype=np.uint8)
+    ptrs = np.array([src.ctypes.data, src.ctypes.data], dtype=np.uint64)
+    lens = np.array([64, 64], dtype=np.int64)
+    ring = np.zeros(4096, dtype=np.uint8)
+    fake_dev = C.c_void_p(0x1000)
+
+    def call(off, slot=1024, slots=4, threads=2, n=2):
+        o = np.array(off, dtype=np.int64)
+        return L.dctd_h2d_rows_staged(ptrs.ctypes.data, lens.ctypes.data, n, fake_dev, o.ctypes.data, ring.ctypes.data, slot, slots,
+                                      threads, None)
+    assert call([0, 32]) == _lib.ERR_ARG    # overlapping
+    assert call([128, 0]) < 0               # descending
+    assert call([0, 64], slot=0) < 0
+    assert call([0, 64], slots=1) < 0
+    assert call([0, 64], threads=0) < 0
+    assert call([0, 64], n=0) == 0          # nothing to do
