@@ -19,6 +19,7 @@ KERNELS = [
     ('l1topk', r'l1_thresh_scan_kernelILi16ELi8ELi2ELi4ELi30E', 'VABSDIFF4', 'l1_thresh_scan'),
     ('l1topk', r'l1_stream_fused_kernelILi8ELi7ELi1ELi30ELi0E', 'VABSDIFF4', 'l1_stream_fused'),
     ('l1topk', r'l1_protein_kernelILi16ELi8ELi2ELi4ELi30E', 'VABSDIFF4', 'l1_protein'),
+    ('api', r'gather_kernel', 'LDG', 'gather'),
 ]
 KEY = ['UBLKCP', 'SYNCS', 'VABSDIFF4', 'FFMA2', 'FADD2', 'FMUL2', 'LDS.128', 'LDS.64', 'F2F.F64.F32', 'DADD', 'DFMA', 'REDUX',
        'NANOSLEEP', 'ATOMG', 'ATOM', 'RED', 'BAR.SYNC', 'MEMBAR', 'UTMALDG', 'UTCHMMA', 'HMMA']
