@@ -277,6 +277,11 @@ def test_planner_fuzz_items_cover_every_domain_row_once(lib, seed):
         pos = int(r[W['r0']])
         for sa, ra, sb_, rb, nrows, l0, g0 in runs_of(r):
             assert nrows > 0 and l0 >= pos
+            # what the TMA producer reads stays inside its source tensors (memcheck is not available on the GPU pool:
+            # the plan's addresses are checked here instead, over random geometries)
+            assert prot_src0[p] <= sa < prot_src0[p] + prot_nsrc[p] and 0 <= ra and ra + nrows <= src_rows[sa]
+            if sb_ >= 0:
+                assert prot_src0[p] <= sb_ < prot_src0[p] + prot_nsrc[p] and 0 <= rb and rb + nrows <= src_rows[sb_]
             if not filler:
                 assert l0 == pos
             for t in range(nrows):
