@@ -408,17 +408,25 @@ def run_ours(args):
         dist.all_reduce(t)
         counts = [int(v) for v in t.tolist()]
     single_s, _ = e2e_run('auto', half_steps, False)
-    # the same batches as plain numpy arrays in pageable memory (what the reference's .cpu().numpy() leaves in
-    # Fingerprint.embed, src/embedding.py:191): host threads stage them through a pinned ring (dctd_h2d_rows_staged)
-    pageable_fps = [(pid, Ln, {k: np.array(v.numpy()) for k, v in emb.items()}) for pid, Ln, emb in host_fps]
 
-    def make_batch_pageable():
-        return [Fingerprint(pid=pid, seq='', embed=emb, domains=[f'1-{Ln}'], quants={}) for pid, Ln, emb in pageable_fps]
+    def measure_pageable():
+        """The same batches as plain numpy arrays in pageable memory (what the reference's .cpu().numpy() leaves in
+        Fingerprint.embed, src/embedding.py:191): host threads stage them through a pinned ring (dctd_h2d_rows_staged).
+        Runs after the device-resident legs: allocating and freeing 1.4 GB of separate numpy arrays leaves the host
+        allocator in a state that slows the interpreter-bound `e2e_device.objects` leg for a while
+        (scripts/objects_regress.py: 3.9 -> 12.4 ms per step right after the allocation)."""
+        from dctdomain_b200.fingerprint import _stage_threads
+        pageable_fps = [(pid, Ln, {k: np.array(v.numpy()) for k, v in emb.items()}) for pid, Ln, emb in host_fps]
 
-    from dctdomain_b200.fingerprint import _stage_threads
-    page_steps = max(3, e2e_steps // 4)
-    page_s, _ = e2e_run('auto', page_steps, True, make_batch_pageable)
-    del pageable_fps
+        def make_batch_pageable():
+            return [Fingerprint(pid=pid, seq='', embed=emb, domains=[f'1-{Ln}'], quants={}) for pid, Ln, emb in pageable_fps]
+
+        page_steps = max(3, e2e_steps // 4)
+        page_s, _ = e2e_run('auto', page_steps, True, make_batch_pageable)
+        return {'value': Be * page_steps * world / page_s, 'unit': 'fingerprints/s', 'host_threads': _stage_threads(),
+                'api': 'the same call on numpy arrays in pageable memory: staged through a pinned ring by host threads '
+                       '(one cudaMemcpyAsync per array from pageable memory: 3.5 k fingerprints/s, gpurun_out/r2h_pageable.log)'}
+
     e2e = {'value': Be * e2e_steps * world / e2e_s, 'unit': 'fingerprints/s', 'h2d_bytes_per_step': int(bytes_all / (e2e_steps * world)),
            'd2h_bytes_per_step': d2h, 'steps': e2e_steps, 'domains_per_step': Be,
            'h2d_GBps_achieved': bytes_all / world / e2e_s / 1e9, 'h2d_GBps_link_pinned_copy': link_gbps,
@@ -429,9 +437,6 @@ def run_ours(args):
                            '(steps x ranks batches in all); h2d_GBps_achieved is the mean over ranks',
            'single_call': {'value': Be * half_steps * world / single_s, 'unit': 'fingerprints/s',
                            'api': 'one quantize_batch(list[Fingerprint]) call after the other (no overlap between calls)'},
-           'pageable': {'value': Be * page_steps * world / page_s, 'unit': 'fingerprints/s', 'host_threads': _stage_threads(),
-                        'api': 'the same call on numpy arrays in pageable memory: staged through a pinned ring by host threads '
-                               '(one cudaMemcpyAsync per array from pageable memory: 3.5 k fingerprints/s, gpurun_out/r2h_pageable.log)'},
            'api': 'dctdomain_b200.fingerprint.quantize_stream(batches of list[Fingerprint]) with pinned host embeddings: '
                   f'quantize_batch per batch, {e2e_depth} batches in flight (H2D of one overlaps the host work of its neighbours); '
                   'every byte of every batch crosses PCIe inside the timed region',
@@ -449,6 +454,7 @@ def run_ours(args):
     e2e_device = None
     if not args.no_fused:
         e2e_device = run_e2e_device(torch, dev, rank, world, barrier, max_over_ranks)
+    e2e['pageable'] = measure_pageable()
 
     # ---- protein-shaped batch: 4 contiguous domains + the global '1-L' domain per protein (what make_db feeds
     #      quantize()); the global fingerprint rides on the domain items, so every row is read once ----
