@@ -227,7 +227,7 @@ def run_ours(args):
     from dctdomain_b200 import _lib
     from dctdomain_b200 import index as dindex
     from dctdomain_b200.fingerprint import Fingerprint, execute_plan, make_plan, quantize_batch, quantize_stream
-    from dctdomain_b200.sharded import ShardedIndex, shard_bounds
+    from dctdomain_b200.sharded import ShardedIndex, shard_bounds, shared_pool
     import synth
 
     rank = int(os.environ.get('RANK', '0'))
@@ -350,7 +350,6 @@ def run_ours(args):
     def make_batch():
         return [Fingerprint(pid=pid, seq='', embed=emb, domains=[f'1-{Ln}'], quants={}) for pid, Ln, emb in host_fps]
 
-    store = dist.distributed_c10d._get_default_store() if world > 1 else None
     e2e_runs = [0]
 
     def e2e_run(staging, steps, pipelined, make_batch=make_batch):
@@ -366,14 +365,9 @@ def run_ours(args):
         mine = [0]
 
         def pool(total):
-            if store is None:
-                for _ in range(total):
-                    mine[0] += 1
-                    yield make_batch()
-            else:
-                while int(store.add(key, 1)) <= total:
-                    mine[0] += 1
-                    yield make_batch()
+            for _ in shared_pool(total, key):
+                mine[0] += 1
+                yield make_batch()
 
         def run(batches):
             if pipelined:

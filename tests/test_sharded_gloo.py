@@ -83,3 +83,40 @@ def test_shard_bounds_cover_everything():
         for g in (1, 2, 4, 8):
             b = [shard_bounds(n, g, r) for r in range(g)]
             assert b[0][0] == 0 and b[-1][1] == n and all(b[i][1] == b[i + 1][0] for i in range(g - 1))
+
+
+def _pool_worker(rank, world, port, out_dir):
+    import sys
+    import time
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path[:0] = [root]
+    from dctdomain_b200.sharded import shared_pool
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    got = []
+    for i in shared_pool(40, 'pool_a'):
+        got.append(i)
+        time.sleep(0.002 * (1 + 3 * rank))          # rank 0 is the fast one
+    second = list(shared_pool(5, 'pool_b'))          # a fresh key starts from 0 again
+    empty = list(shared_pool(0, 'pool_c'))
+    np.savez(os.path.join(out_dir, f'p{rank}.npz'), got=np.array(got, dtype=np.int64), second=np.array(second, dtype=np.int64),
+             empty=np.array(empty, dtype=np.int64))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('world', [2, 3])
+def test_shared_pool_hands_every_index_to_exactly_one_rank(tmp_path, world):
+    """The work queue bench.py's multi-rank e2e uses (and a multi-GPU make_db would): every index once over all ranks,
+    ascending within a rank, the faster rank takes more; without a process group it is range(total)."""
+    from dctdomain_b200.sharded import shared_pool
+    assert list(shared_pool(7, 'no_group')) == list(range(7))
+    mp.spawn(_pool_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    parts = [np.load(tmp_path / f'p{r}.npz') for r in range(world)]
+    allgot = np.concatenate([z['got'] for z in parts])
+    assert sorted(allgot.tolist()) == list(range(40))
+    for z in parts:
+        assert np.all(np.diff(z['got']) > 0) and len(z['empty']) == 0
+    assert len(parts[0]['got']) > len(parts[-1]['got'])
+    assert sorted(np.concatenate([z['second'] for z in parts]).tolist()) == list(range(5))
